@@ -1,0 +1,133 @@
+"""ctypes view of oracle/_ref/libyolo2ref_{scalar,fast}.so -- the UNMODIFIED reference CPU path.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+``--impl reference`` legs, never by the product package (yolo2_light_b200/).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+
+# reference enums (additionally.h:68-70, :376-403)
+LAYER_TYPES = ["CONVOLUTIONAL", "DECONVOLUTIONAL", "CONNECTED", "MAXPOOL", "SOFTMAX", "DETECTION", "DROPOUT", "CROP",
+               "ROUTE", "COST", "NORMALIZATION", "AVGPOOL", "LOCAL", "SHORTCUT", "ACTIVE", "RNN", "GRU", "CRNN",
+               "BATCHNORM", "NETWORK", "XNOR", "REGION", "YOLO", "UPSAMPLE", "REORG", "BLANK"]
+ACTIVATIONS = ["LOGISTIC", "RELU", "RELIE", "LINEAR", "RAMP", "TANH", "PLSE", "LEAKY", "ELU", "LOGGY", "STAIR",
+               "HARDTAN", "LHTAN", "SELU"]
+INT_FIELDS = ["type", "activation", "batch_normalize", "batch", "h", "w", "c", "n", "size", "stride", "pad",
+              "out_h", "out_w", "out_c", "inputs", "outputs", "xnor", "binary", "quantized", "index",
+              "classes", "coords", "softmax", "total", "reverse", "lda_align", "new_lda", "bit_align",
+              "align_bit_weights_size", "dontload", "dontloadscales", "use_bin_output", "max_boxes", "groups"]
+
+
+def lib_path(kind: str = "scalar") -> str:
+    return os.path.join(REF_DIR, f"libyolo2ref_{kind}.so")
+
+
+def available(kind: str = "scalar") -> bool:
+    return os.path.exists(lib_path(kind))
+
+
+_libs = {}
+
+
+def _load(kind: str):
+    if kind in _libs:
+        return _libs[kind]
+    lib = C.CDLL(lib_path(kind), mode=os.RTLD_LOCAL if hasattr(os, "RTLD_LOCAL") else 0)
+    lib.refh_create.restype = C.c_void_p
+    lib.refh_create.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int]
+    lib.refh_num_layers.argtypes = [C.c_void_p]
+    lib.refh_net_ints.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    lib.refh_net_input_calibration.restype = C.POINTER(C.c_float)
+    lib.refh_net_input_calibration.argtypes = [C.c_void_p]
+    lib.refh_layer_ints.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    lib.refh_layer_floats.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
+    lib.refh_layer_ptr.restype = C.c_void_p
+    lib.refh_layer_ptr.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+    lib.refh_predict.restype = C.POINTER(C.c_float)
+    lib.refh_predict.argtypes = [C.c_void_p, C.c_void_p]
+    lib.refh_forward_layer.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.refh_time_predict.restype = C.c_double
+    lib.refh_time_predict.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.refh_get_boxes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_int,
+                                   C.POINTER(C.c_int)]
+    lib.refh_set_quiet.argtypes = [C.c_int]
+    _libs[kind] = lib
+    return lib
+
+
+class RefNet:
+    """The reference's ``network`` after the main.c:160-171 preparation sequence."""
+
+    def __init__(self, cfg: str, weights: Optional[str], batch: int = 1, quantized: int = 0, prep: int = 7,
+                 kind: str = "scalar"):
+        self.lib = _load(kind)
+        self.h = self.lib.refh_create(cfg.encode(), (weights or "").encode(), batch, quantized, prep)
+        ints = (C.c_int * 16)()
+        self.lib.refh_net_ints(self.h, ints)
+        self.n, self.batch, self.height, self.width, self.channels = ints[0], ints[1], ints[2], ints[3], ints[4]
+        self.inputs, self.outputs, self.input_calibration_size = ints[5], ints[6], ints[7]
+        self.quantized = quantized
+        self.layers = [self._layer(i) for i in range(self.n)]
+
+    def _layer(self, i: int) -> dict:
+        ints = (C.c_int * 40)()
+        self.lib.refh_layer_ints(self.h, i, ints)
+        d = {k: ints[j] for j, k in enumerate(INT_FIELDS)}
+        d["type_name"] = LAYER_TYPES[d["type"]]
+        d["activation_name"] = ACTIVATIONS[d["activation"]]
+        fl = (C.c_float * 8)()
+        self.lib.refh_layer_floats(self.h, i, fl)
+        d.update(weights_quant_multipler=fl[0], input_quant_multipler=fl[1], output_multipler=fl[2],
+                 scale=fl[3], bflops=fl[4])
+        return d
+
+    def input_calibration(self) -> np.ndarray:
+        p = self.lib.refh_net_input_calibration(self.h)
+        if not p or self.input_calibration_size == 0:
+            return np.zeros(0, np.float32)
+        return np.ctypeslib.as_array(p, shape=(self.input_calibration_size,)).copy()
+
+    def array(self, i: int, what: str, count: int, dtype=np.float32) -> Optional[np.ndarray]:
+        p = self.lib.refh_layer_ptr(self.h, i, what.encode())
+        if not p:
+            return None
+        buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(p)
+        return np.frombuffer(buf, dtype=dtype, count=count).copy()
+
+    def output(self, i: int) -> np.ndarray:
+        L = self.layers[i]
+        a = self.array(i, "output", L["outputs"] * L["batch"])
+        if L["type_name"] in ("CONVOLUTIONAL", "MAXPOOL", "ROUTE", "UPSAMPLE", "SHORTCUT", "REORG", "YOLO"):
+            return a.reshape(L["batch"], L["out_c"], L["out_h"], L["out_w"])
+        return a.reshape(L["batch"], -1)
+
+    def predict(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        assert x.size == self.inputs * self.batch, (x.shape, self.inputs, self.batch)
+        self.lib.refh_predict(self.h, x.ctypes.data_as(C.c_void_p))
+        return self.output(self.n - 1)
+
+    def forward_layer(self, i: int, x: np.ndarray, use_q_rule: Optional[bool] = None) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        q = self.quantized if use_q_rule is None else int(use_q_rule)
+        self.lib.refh_forward_layer(self.h, i, x.ctypes.data_as(C.c_void_p), q)
+        return self.output(i)
+
+    def time_predict(self, x: np.ndarray, reps: int = 1) -> float:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        return float(self.lib.refh_time_predict(self.h, x.ctypes.data_as(C.c_void_p), reps))
+
+    def get_boxes(self, w: int, h: int, thresh: float, nms: float, max_out: int = 200000):
+        classes = self.layers[-1]["classes"]
+        out = np.zeros((max_out, 6 + classes), np.float32)
+        cl = C.c_int()
+        n = self.lib.refh_get_boxes(self.h, w, h, thresh, nms, out.ctypes.data_as(C.c_void_p), max_out, C.byref(cl))
+        return out[:min(n, max_out)]
