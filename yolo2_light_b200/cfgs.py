@@ -36,7 +36,24 @@ def _net(width: int, height: int, calib: Optional[Sequence[float]] = None) -> Se
     return ("net", o)
 
 
+_WIDTH_DIV = 1   # >1: thin test variants (same topology, filters // div) -- see slim()
+
+
+def slim(builder, div: int, *args, **kw) -> List[Section]:
+    """Build a model with every BN convolution's filter count divided by ``div`` (detection heads keep their
+    size).  Same layer graph, ~div^2 fewer weights: used by the CPU tests, where the full-width models only cost
+    time (this container page-faults at ~50 MB/s)."""
+    global _WIDTH_DIV
+    old, _WIDTH_DIV = _WIDTH_DIV, div
+    try:
+        return builder(*args, **kw)
+    finally:
+        _WIDTH_DIV = old
+
+
 def _conv(filters: int, size: int, stride: int = 1, bn: bool = True, act: str = "leaky", **extra) -> Section:
+    if bn and _WIDTH_DIV > 1:
+        filters = max(filters // _WIDTH_DIV, 4)
     o: Dict[str, str] = {}
     for k, v in extra.items():
         o[k] = str(v)

@@ -1,0 +1,320 @@
+// yb_capi.cpp -- the extern "C" surface declared in include/yolo2_light_b200.h
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "yb_engine.h"
+#include "yb_model.h"
+
+using namespace yb;
+
+static thread_local std::string g_last_error;
+static int g_abort_on_error = 1;
+
+static void report(const std::string &msg) {
+    g_last_error = msg;
+    if (g_abort_on_error) {   // reference convention: print and die (additionally.c:1595-1600)
+        fprintf(stderr, "yolo2_light_b200: %s\n", msg.c_str());
+        abort();
+    }
+}
+
+#define YB_TRY try {
+#define YB_CATCH(retval)                                                       \
+    }                                                                          \
+    catch (const yb::Error &e) { report(e.msg); return retval; }               \
+    catch (const std::exception &e) { report(e.what()); return retval; }
+#define YB_CATCH_VOID                                                          \
+    }                                                                          \
+    catch (const yb::Error &e) { report(e.msg); return; }                      \
+    catch (const std::exception &e) { report(e.what()); return; }
+
+static Engine *get_engine(yb_network *n, int quantized, bool upload = true) {
+    Network &net = n->net;
+    const int slot = quantized ? 1 : 0;
+    if (!net.engine[slot]) {
+        EngineOptions opt;
+        opt.device = net.device;
+        opt.precision = net.precision;
+        opt.qrule = quantized != 0;
+        opt.upload = upload;
+        const char *nf = getenv("YB_NO_FUSE");
+        opt.fuse = !(nf && nf[0] == '1') && net.fuse;
+        opt.keep_counts = net.keep_counts;
+        opt.q_index_offset = net.q_index_offset;
+        net.engine[slot] = build_engine(&net, opt);
+    }
+    return net.engine[slot].get();
+}
+
+extern "C" {
+
+void yb_set_abort_on_error(int on) { g_abort_on_error = on; }
+const char *yb_last_error(void) { return g_last_error.c_str(); }
+const char *yb_version(void) { return "yolo2_light_b200 0.1 (sm_100a)"; }
+
+yb_network *yb_parse_network_cfg(const char *filename, int batch, int quantized) {
+    YB_TRY
+    Network *net = parse_network_cfg(filename, batch, quantized);
+    yb_network *h = new yb_network();
+    h->net = std::move(*net);
+    delete net;
+    return h;
+    YB_CATCH(nullptr)
+}
+
+int yb_load_weights_upto(yb_network *net, const char *filename, int cutoff) {
+    YB_TRY
+    load_weights_upto(&net->net, filename, cutoff);
+    return 0;
+    YB_CATCH(-1)
+}
+
+void yb_fuse_conv_batchnorm(yb_network *net) { YB_TRY fuse_conv_batchnorm(&net->net); YB_CATCH_VOID }
+void yb_calculate_binary_weights(yb_network *net) { YB_TRY calculate_binary_weights(&net->net); YB_CATCH_VOID }
+void yb_quantinization_and_get_multipliers(yb_network *net) {
+    YB_TRY quantinization_and_get_multipliers(&net->net); YB_CATCH_VOID
+}
+
+yb_network *yb_network_from_layers(const yb_layer_desc *layers, int n_layers, int batch, int h, int w, int c,
+                                   int quantized) {
+    YB_TRY
+    yb_network *hnd = new yb_network();
+    Network &net = hnd->net;
+    net.batch = batch; net.h = h; net.w = w; net.c = c; net.inputs = h * w * c; net.quantized = quantized;
+    net.layers.resize(n_layers);
+    for (int i = 0; i < n_layers; ++i) {
+        const yb_layer_desc &d = layers[i];
+        Layer &l = net.layers[i];
+        l.type = d.type; l.activation = d.activation; l.batch_normalize = d.batch_normalize;
+        l.h = d.h; l.w = d.w; l.c = d.c; l.n = d.n; l.size = d.size; l.stride = d.stride; l.pad = d.pad;
+        l.out_h = d.out_h; l.out_w = d.out_w; l.out_c = d.out_c;
+        l.xnor = d.xnor; l.quantized = d.quantized; l.index = d.index;
+        l.classes = d.classes; l.coords = d.coords; l.softmax = d.softmax; l.total = d.total;
+        l.reverse = d.reverse; l.scale = d.scale;
+        l.inputs = l.h * l.w * l.c;
+        switch (l.type) {
+        case YB_CONVOLUTIONAL: {
+            const size_t nw = (size_t)l.n * l.c * l.size * l.size;
+            if (!d.weights || !d.biases) fatal_throw("from_layers: conv without weights/biases");
+            l.weights.assign(d.weights, d.weights + nw);
+            l.biases.assign(d.biases, d.biases + l.n);
+            if (l.batch_normalize) {
+                if (!d.scales || !d.rolling_mean || !d.rolling_variance) fatal_throw("from_layers: BN arrays missing");
+                l.scales.assign(d.scales, d.scales + l.n);
+                l.rolling_mean.assign(d.rolling_mean, d.rolling_mean + l.n);
+                l.rolling_variance.assign(d.rolling_variance, d.rolling_variance + l.n);
+            }
+            if (d.weights_int8) {
+                l.weights_int8.assign(d.weights_int8, d.weights_int8 + nw);
+                l.weights_quant_multipler = d.weights_quant_multipler;
+                l.input_quant_multipler = d.input_quant_multipler;
+                l.has_int8 = true;
+            }
+            if (d.mean_arr) { l.mean_arr.assign(d.mean_arr, d.mean_arr + l.n); l.has_mean_arr = true; }
+            l.outputs = l.out_h * l.out_w * l.out_c;
+            break;
+        }
+        case YB_ROUTE:
+            if (!d.input_layers) fatal_throw("from_layers: route without input_layers");
+            l.input_layers.assign(d.input_layers, d.input_layers + l.n);
+            l.outputs = 0;
+            for (int s : l.input_layers) {
+                if (s < 0 || s >= i) fatal_throw("from_layers: bad route index");
+                l.input_sizes.push_back(net.layers[s].outputs);
+                l.outputs += net.layers[s].outputs;
+            }
+            break;
+        case YB_YOLO:
+            if (d.mask) l.mask.assign(d.mask, d.mask + l.n);
+            if (d.anchors) l.anchors.assign(d.anchors, d.anchors + 2 * (size_t)l.total);
+            l.outputs = l.h * l.w * l.n * (l.classes + 4 + 1);
+            break;
+        case YB_REGION:
+            if (d.anchors) l.anchors.assign(d.anchors, d.anchors + 2 * (size_t)l.n);
+            l.outputs = l.h * l.w * l.n * (l.classes + l.coords + 1);
+            break;
+        default:
+            l.outputs = l.out_h * l.out_w * l.out_c;
+            break;
+        }
+    }
+    return hnd;
+    YB_CATCH(nullptr)
+}
+
+void yb_free_network(yb_network *net) { delete net; }
+
+int yb_network_num_layers(const yb_network *net) { return (int)net->net.layers.size(); }
+
+void yb_network_dims(const yb_network *n, int *o) {
+    const Network &net = n->net;
+    o[0] = (int)net.layers.size(); o[1] = net.batch; o[2] = net.h; o[3] = net.w; o[4] = net.c; o[5] = net.inputs;
+    o[6] = net.layers.empty() ? 0 : net.layers.back().outputs;
+    o[7] = (int)net.input_calibration.size();
+}
+
+int yb_network_layer(const yb_network *n, int i, yb_layer_desc *d) {
+    if (i < 0 || i >= (int)n->net.layers.size()) return -1;
+    const Layer &l = n->net.layers[i];
+    memset(d, 0, sizeof(*d));
+    d->type = l.type; d->activation = l.activation; d->batch_normalize = l.batch_normalize;
+    d->h = l.h; d->w = l.w; d->c = l.c; d->n = l.n; d->size = l.size; d->stride = l.stride; d->pad = l.pad;
+    d->out_h = l.out_h; d->out_w = l.out_w; d->out_c = l.out_c;
+    d->xnor = l.xnor; d->quantized = l.quantized; d->index = l.index;
+    d->classes = l.classes; d->coords = l.coords; d->softmax = l.softmax; d->total = l.total;
+    d->reverse = l.reverse; d->scale = l.scale;
+    d->input_layers = l.input_layers.empty() ? nullptr : l.input_layers.data();
+    d->mask = l.mask.empty() ? nullptr : l.mask.data();
+    d->anchors = l.anchors.empty() ? nullptr : l.anchors.data();
+    d->weights = l.weights.empty() ? nullptr : l.weights.data();
+    d->biases = l.biases.empty() ? nullptr : l.biases.data();
+    d->scales = l.scales.empty() ? nullptr : l.scales.data();
+    d->rolling_mean = l.rolling_mean.empty() ? nullptr : l.rolling_mean.data();
+    d->rolling_variance = l.rolling_variance.empty() ? nullptr : l.rolling_variance.data();
+    d->weights_int8 = l.has_int8 ? l.weights_int8.data() : nullptr;
+    d->weights_quant_multipler = l.weights_quant_multipler;
+    d->input_quant_multipler = l.input_quant_multipler;
+    d->mean_arr = l.has_mean_arr ? l.mean_arr.data() : nullptr;
+    return 0;
+}
+
+int yb_network_layer_outputs(const yb_network *n, int i) {
+    if (i < 0 || i >= (int)n->net.layers.size()) return -1;
+    return n->net.layers[i].outputs;
+}
+
+const float *yb_network_input_calibration(const yb_network *n, int *count) {
+    if (count) *count = (int)n->net.input_calibration.size();
+    return n->net.input_calibration.empty() ? nullptr : n->net.input_calibration.data();
+}
+
+void yb_set_batch_network(yb_network *net, int batch) { set_batch(&net->net, batch); }
+
+int yb_network_set_device(yb_network *n, int device) {
+    n->net.device = device;
+    n->net.engine[0].reset(); n->net.engine[1].reset();
+    return 0;
+}
+int yb_network_set_precision(yb_network *n, int precision) {
+    if (precision != YB_PREC_BF16_TC && precision != YB_PREC_FP32) { report("bad precision"); return -1; }
+    n->net.precision = precision;
+    n->net.engine[0].reset(); n->net.engine[1].reset();
+    return 0;
+}
+/* diagnostic switches (tests): fusion on/off, keep raw integer results, INT8 rule index offset */
+int yb_network_set_option(yb_network *n, const char *name, int value) {
+    Network &net = n->net;
+    if (!strcmp(name, "fuse")) net.fuse = value != 0;
+    else if (!strcmp(name, "keep_counts")) net.keep_counts = value != 0;
+    else if (!strcmp(name, "q_index_offset")) net.q_index_offset = value;
+    else { report(std::string("unknown option ") + name); return -1; }
+    net.engine[0].reset(); net.engine[1].reset();
+    return 0;
+}
+
+static float *predict_common(yb_network *n, const float *input, int quantized) {
+    Engine *e = get_engine(n, quantized);
+    engine_upload_input(e, input, nullptr);
+    engine_forward(e, nullptr, nullptr);
+    engine_download_outputs(e, &n->net, nullptr);
+    n->net.last_launches = engine_num_launches(e);
+    return n->net.layers.back().output;
+}
+
+float *yb_network_predict(yb_network *n, const float *input) {
+    YB_TRY return predict_common(n, input, 0); YB_CATCH(nullptr)
+}
+float *yb_network_predict_quantized(yb_network *n, const float *input) {
+    YB_TRY return predict_common(n, input, 1); YB_CATCH(nullptr)
+}
+
+const float *yb_network_layer_output(const yb_network *n, int i, int *count) {
+    if (i < 0 || i >= (int)n->net.layers.size()) return nullptr;
+    if (count) *count = (int)n->net.layers[i].output_count;
+    return n->net.layers[i].output;
+}
+
+int yb_network_forward_device(yb_network *n, const void *d_input, int quantized, void *stream) {
+    YB_TRY
+    Engine *e = get_engine(n, quantized);
+    engine_forward(e, d_input, stream);
+    n->net.last_launches = engine_num_launches(e);
+    return 0;
+    YB_CATCH(-1)
+}
+int yb_network_sync_outputs(yb_network *n, int quantized, void *stream) {
+    YB_TRY
+    Engine *e = get_engine(n, quantized);
+    engine_download_outputs(e, &n->net, stream);
+    return 0;
+    YB_CATCH(-1)
+}
+
+int yb_network_fetch_layer(yb_network *n, int i, int quantized, float *dst) {
+    YB_TRY
+    Engine *e = get_engine(n, quantized);
+    engine_fetch_layer(e, &n->net, i, dst);
+    return 0;
+    YB_CATCH(-1)
+}
+int yb_network_fetch_counts(yb_network *n, int i, int quantized, int32_t *dst, size_t count) {
+    YB_TRY
+    Engine *e = get_engine(n, quantized);
+    return engine_fetch_counts(e, i, dst, count);
+    YB_CATCH(-1)
+}
+
+int yb_forward_convolutional_layer(yb_network *n, int i, int variant, const float *input, float *output) {
+    YB_TRY
+    const Network &src = n->net;
+    if (i < 0 || i >= (int)src.layers.size() || src.layers[i].type != YB_CONVOLUTIONAL)
+        fatal_throw("yb_forward_convolutional_layer: not a convolutional layer");
+    yb_network tmp;
+    Network &t = tmp.net;
+    const Layer &l = src.layers[i];
+    t.batch = src.batch; t.h = l.h; t.w = l.w; t.c = l.c; t.inputs = l.h * l.w * l.c;
+    t.device = src.device; t.precision = src.precision; t.fuse = false;
+    t.q_index_offset = i;
+    t.layers.push_back(l);
+    t.layers[0].output = nullptr;
+    Engine *e = get_engine(&tmp, variant);
+    engine_upload_input(e, input, nullptr);
+    engine_forward(e, nullptr, nullptr);
+    engine_fetch_layer(e, &t, 0, output);
+    return 0;
+    YB_CATCH(-1)
+}
+
+int yb_network_weight_arena(yb_network *n, int quantized, int upload, void **d_ptr, size_t *bytes) {
+    YB_TRY
+    Engine *e = get_engine(n, quantized, upload != 0);
+    engine_weight_arena(e, d_ptr, bytes);
+    return 0;
+    YB_CATCH(-1)
+}
+
+int yb_network_last_launches(const yb_network *n) { return n->net.last_launches; }
+
+int yb_network_profile(yb_network *n, int quantized, const void *d_input, int *layer_idx, int *op_kind,
+                       float *ms, int max) {
+    YB_TRY
+    Engine *e = get_engine(n, quantized);
+    return engine_profile(e, d_input, layer_idx, op_kind, ms, max);
+    YB_CATCH(-1)
+}
+const char *yb_op_kind_name(int k) { return op_kind_name(k); }
+
+int yb_get_network_boxes(const yb_network *n, int b, int w, int h, float thresh, float nms, int relative,
+                         int letter, float *out, int max_rows) {
+    YB_TRY
+    return get_boxes(&n->net, b, w, h, thresh, nms, relative, letter, out, max_rows);
+    YB_CATCH(-1)
+}
+
+/* pinned host memory for the end-to-end path (input images) */
+void *yb_alloc_pinned(size_t bytes);
+void yb_free_pinned(void *p);
+
+}  // extern "C"

@@ -1,0 +1,19 @@
+// yb_conv_tc.cuh -- interface of the tensor-core (tcgen05 / TMEM / TMA) implicit-GEMM convolutions
+// (implemented in yb_conv_tc.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "yb_kernels.cuh"
+#include "yb_model.h"
+
+namespace yb {
+
+// non-zero if the bf16 tcgen05 kernel takes this layer (input view `in`, bf16 or f32 output)
+int tc_conv_supported(const Layer &l, const TV &in, bool out_bf16);
+// builds the per-layer launch state (TMA tensor maps, tile schedule); throws yb::Error on failure
+void *tc_make_plan(const Layer &l, const TV &in, const TV &out, bool out_bf16, const TV &res, bool res_bf16,
+                   int act2, const void *d_weights_bf16, int ldn, const float *d_bias);
+void tc_launch(void *plan, cudaStream_t s);
+void tc_free_plan(void *plan);
+
+}  // namespace yb

@@ -1,0 +1,769 @@
+// yb_engine.cu -- builds and runs the device execution plan of a prepared network.
+//
+// Mirrors the layer loop of the reference (yolov2_forward_network_cpu, src/yolov2_forward_network.c:581-628 and
+// yolov2_forward_network_q, src/yolov2_forward_network_quantized.c:1027-1089) as a flat list of kernel
+// launches with pre-resolved device pointers, replayed as a CUDA graph.  See yb_kernels.cuh for the device
+// layout.  No CPU fallback: everything here requires a compute-capability-10.x device.
+#include "yb_engine.h"
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "yb_conv_tc.cuh"
+#include "yb_kernels.cuh"
+
+namespace yb {
+
+#define CUDA_OK(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t _e = (call);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            fatal_throw(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + __FILE__ + ":" + \
+                        std::to_string(__LINE__) + " (" #call ")");                                     \
+    } while (0)
+
+const char *op_kind_name(int k) {
+    static const char *names[] = {"input", "conv_simt", "conv_tc", "binarize", "conv_xnor", "quantize",
+                                  "conv_int8", "maxpool", "upsample", "shortcut", "route_copy", "reorg",
+                                  "yolo", "region", "conv_tc_i8"};
+    return (k >= 0 && k < 15) ? names[k] : "?";
+}
+
+enum { DT_F32 = 0, DT_BF16 = 1, DT_S8 = 2, DT_BITS = 3 };
+static inline size_t dt_size(int dt) { return dt == DT_F32 ? 4 : dt == DT_BF16 ? 2 : dt == DT_S8 ? 1 : 4; }
+
+struct Op {
+    int kind;
+    int layer;
+    std::function<void(cudaStream_t)> launch;
+};
+
+struct ConvWeights {   // offsets into the weight arena
+    size_t w_f32 = (size_t)-1, w_bf16 = (size_t)-1, w_s8 = (size_t)-1, w_bits = (size_t)-1;
+    size_t bias = (size_t)-1, mean = (size_t)-1;
+    int ldw = 0;      // f32 [K][ldw]
+    int ldn = 0;      // rows of the [ldn][...] layouts
+    int cpad = 0;     // padded channels of the s8 / bits / bf16 layouts
+};
+
+struct Engine {
+    EngineOptions opt;
+    int batch = 0;
+    int act_dt = DT_F32;
+    cudaStream_t stream = nullptr;
+    char *act_arena = nullptr; size_t act_bytes = 0;
+    char *w_arena = nullptr;   size_t w_bytes = 0;
+    float *d_input = nullptr;  size_t input_count = 0;
+    std::vector<TV> out_tv;            // per layer (base == nullptr: no NHWC output)
+    std::vector<int> out_dt;
+    std::vector<float *> d_final;      // yolo / region device outputs
+    std::vector<float *> h_final;      // pinned host mirrors
+    std::vector<size_t> final_count;
+    std::vector<int32_t *> d_counts;   // optional raw integer results per conv layer
+    std::vector<size_t> counts_count;
+    std::vector<Op> ops;
+    TV in0{};
+    int in0_dt = DT_F32;
+    cudaGraphExec_t graph_exec = nullptr;
+    bool graph_failed = false;
+    std::vector<void *> tc_plans;      // opaque per-layer state of the tensor-core path (tensor maps)
+    ~Engine();
+};
+
+Engine::~Engine() {
+    cudaSetDevice(opt.device);
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    for (float *p : h_final) if (p) cudaFreeHost(p);
+    for (float *p : d_final) if (p) cudaFree(p);
+    for (int32_t *p : d_counts) if (p) cudaFree(p);
+    for (void *p : tc_plans) tc_free_plan(p);
+    if (act_arena) cudaFree(act_arena);
+    if (w_arena) cudaFree(w_arena);
+    if (d_input) cudaFree(d_input);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int grid_for(long total, int block = 256) {
+    long g = (total + block - 1) / block;
+    const long cap = 148L * 32;   // grid-stride kernels: a few waves of the 148 SMs
+    return (int)std::max<long>(1, std::min(g, cap));
+}
+
+static TV make_tv(char *base, int N, int H, int W, int C, int ldc, int P, int dt, int coff) {
+    TV t;
+    t.base = base + (size_t)coff * dt_size(dt);
+    t.N = N; t.H = H; t.W = W; t.C = C; t.ldc = ldc; t.P = P; t.Hp = H + 2 * P; t.Wp = W + 2 * P;
+    return t;
+}
+static size_t tv_bytes(int N, int H, int W, int ldc, int P, int dt) {
+    return (size_t)N * (H + 2 * P) * (W + 2 * P) * ldc * dt_size(dt);
+}
+
+// which layers read layer j's output
+static std::vector<std::vector<int>> consumers_of(const Network &net) {
+    const int nl = (int)net.layers.size();
+    std::vector<std::vector<int>> cons(nl);
+    for (int i = 0; i < nl; ++i) {
+        const Layer &l = net.layers[i];
+        if (l.type == YB_ROUTE) {
+            for (int s : l.input_layers) cons[s].push_back(i);
+        } else if (l.type != YB_BLANK) {
+            if (i > 0) cons[i - 1].push_back(i);
+            if (l.type == YB_SHORTCUT) cons[l.index].push_back(i);
+        }
+    }
+    return cons;
+}
+
+template <typename F>
+static void dispatch_dt(int dt, F &&f) {
+    if (dt == DT_F32) f((float *)nullptr);
+    else f((__nv_bfloat16 *)nullptr);
+}
+
+std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        fatal_throw("yolo2_light_b200: no CUDA device -- this library has no CPU fallback");
+    CUDA_OK(cudaSetDevice(opt.device));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, opt.device));
+    if (prop.major != 10)
+        fatal_throw(std::string("yolo2_light_b200: device '") + prop.name + "' is compute capability " +
+                    std::to_string(prop.major) + "." + std::to_string(prop.minor) +
+                    "; this build contains sm_100a code only");
+
+    auto e = std::make_shared<Engine>();
+    e->opt = opt;
+    e->batch = net->batch;
+    const int B = net->batch;
+    const int nl = (int)net->layers.size();
+    if (nl == 0) fatal_throw("empty network");
+    CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+
+    bool any_xnor = false;
+    for (const Layer &l : net->layers) {
+        if (l.type != YB_CONVOLUTIONAL) continue;
+        if (l.batch_normalize) fatal_throw("engine: batch-norm not folded -- call yb_fuse_conv_batchnorm first");
+        if (l.xnor) {
+            any_xnor = true;
+            if (!l.has_mean_arr) fatal_throw("engine: xnor layer without mean_arr -- call yb_calculate_binary_weights first");
+            if (!(l.stride == 1 && l.pad == 1))
+                fatal_throw("engine: xnor convolution with stride != 1 or pad != 1 is not supported (the reference's "
+                            "fallback for it, binarize_cpu at additionally.c:128, feeds an all-zero input)");
+        }
+        if (opt.qrule && !l.has_int8)
+            fatal_throw("engine: -quantized rule without int8 weights -- call yb_quantinization_and_get_multipliers first");
+    }
+    // f32 activations whenever an integer path must see exactly the reference's inputs
+    const bool exact = opt.qrule || any_xnor || opt.precision == YB_PREC_FP32;
+    e->act_dt = exact ? DT_F32 : DT_BF16;
+    const int ADT = e->act_dt;
+
+    auto conv_variant = [&](int i) -> int {   // 0 fp32, 1 xnor, 2 int8
+        const Layer &l = net->layers[i];
+        if (opt.qrule && (i + opt.q_index_offset) >= 1 && l.activation != YB_LINEAR) return 2;
+        if (l.xnor) return 1;
+        return 0;
+    };
+
+    const auto cons = consumers_of(*net);
+
+    // ---- fusion plan: conv i + same-shape shortcut i+1 whose only reader is that shortcut -------------
+    std::vector<int> fused_into(nl, -1);   // conv i writes layer fused_into[i]'s output
+    std::vector<char> is_fused_sc(nl, 0);
+    if (opt.fuse) {
+        for (int i = 0; i + 1 < nl; ++i) {
+            const Layer &l = net->layers[i], &s = net->layers[i + 1];
+            if (l.type != YB_CONVOLUTIONAL || s.type != YB_SHORTCUT) continue;
+            if (conv_variant(i) != 0) continue;
+            if (cons[i].size() != 1 || cons[i][0] != i + 1) continue;
+            if (s.index == i) continue;
+            if (!(s.w == s.out_w && s.h == s.out_h && s.c == s.out_c)) continue;
+            fused_into[i] = i + 1;
+            is_fused_sc[i + 1] = 1;
+        }
+    }
+
+    // ---- output placement --------------------------------------------------------------------------
+    // pass 1: decide dtype + home of every layer output (own buffer, or a channel slice of a concat buffer)
+    struct Home { int owner = -1; int coff = 0; int ldc = 0; };   // owner: layer whose buffer holds it
+    std::vector<Home> home(nl);
+    e->out_dt.assign(nl, ADT);
+    auto has_nhwc_out = [&](int i) {
+        const Layer &l = net->layers[i];
+        if (l.type == YB_YOLO || l.type == YB_REGION || l.type == YB_BLANK) return false;
+        if (fused_into[i] >= 0) return false;
+        if (l.out_h <= 0 || l.out_w <= 0 || l.out_c <= 0) return false;
+        return true;
+    };
+    for (int i = 0; i < nl; ++i) {
+        const Layer &l = net->layers[i];
+        if (l.type == YB_CONVOLUTIONAL && !cons[i].empty()) {
+            bool all_final = true;
+            for (int c : cons[i]) if (net->layers[c].type != YB_YOLO && net->layers[c].type != YB_REGION) all_final = false;
+            if (all_final) e->out_dt[i] = DT_F32;   // detection heads stay f32 (bf16 would cost ~1e-3 rel by itself)
+        }
+        if (l.type == YB_CONVOLUTIONAL && cons[i].empty()) e->out_dt[i] = DT_F32;
+    }
+    if (opt.fuse) {
+        for (int r = 0; r < nl; ++r) {
+            const Layer &l = net->layers[r];
+            if (l.type != YB_ROUTE || l.n < 2 || l.out_c <= 0) continue;
+            int off = 0;
+            for (int k = 0; k < l.n; ++k) {
+                const int j = l.input_layers[k];
+                const Layer &src = net->layers[j];
+                const bool ok = has_nhwc_out(j) && home[j].owner < 0 && src.type != YB_ROUTE &&
+                                e->out_dt[j] == ADT;
+                if (ok) { home[j].owner = r; home[j].coff = off; home[j].ldc = l.out_c; }
+                off += src.out_c;
+            }
+        }
+    }
+    // pass 2: sizes + arena offsets
+    std::vector<size_t> buf_off(nl, (size_t)-1);
+    size_t act_total = 0;
+    const int P = 1;
+    auto own_buffer = [&](int i) {
+        const Layer &l = net->layers[i];
+        buf_off[i] = act_total;
+        act_total += align_up(tv_bytes(B, l.out_h, l.out_w, l.out_c, P, e->out_dt[i]), 1024);
+    };
+    const size_t in0_off = act_total;
+    e->in0_dt = ADT;
+    act_total += align_up(tv_bytes(B, net->h, net->w, net->c, P, ADT), 1024);
+    for (int i = 0; i < nl; ++i) {
+        const Layer &l = net->layers[i];
+        if (!has_nhwc_out(i)) continue;
+        if (l.type == YB_ROUTE && l.n == 1 && opt.fuse) continue;   // pure alias
+        if (home[i].owner >= 0) continue;                           // lives inside a concat buffer
+        own_buffer(i);
+    }
+    // side buffers of the integer paths
+    std::vector<size_t> side_off(nl, (size_t)-1);
+    std::vector<int> side_ld(nl, 0);
+    for (int i = 0; i < nl; ++i) {
+        const Layer &l = net->layers[i];
+        if (l.type != YB_CONVOLUTIONAL) continue;
+        const int v = conv_variant(i);
+        if (v == 1) {
+            side_ld[i] = (l.c + 31) / 32;
+            side_off[i] = act_total;
+            act_total += align_up(tv_bytes(B, l.h, l.w, side_ld[i], P, DT_BITS), 1024);
+        } else if (v == 2) {
+            side_ld[i] = (int)align_up(l.c, 16);
+            side_off[i] = act_total;
+            act_total += align_up(tv_bytes(B, l.h, l.w, side_ld[i], P, DT_S8), 1024);
+        }
+    }
+    e->act_bytes = act_total;
+    CUDA_OK(cudaMalloc(&e->act_arena, act_total));
+    CUDA_OK(cudaMemsetAsync(e->act_arena, 0, act_total, e->stream));   // zero borders, once
+
+    e->in0 = make_tv(e->act_arena + in0_off, B, net->h, net->w, net->c, net->c, P, ADT, 0);
+    e->out_tv.assign(nl, TV{});
+    for (int i = 0; i < nl; ++i) {
+        const Layer &l = net->layers[i];
+        if (!has_nhwc_out(i)) continue;
+        if (l.type == YB_ROUTE && l.n == 1 && opt.fuse) {
+            e->out_tv[i] = e->out_tv[l.input_layers[0]];
+            e->out_dt[i] = e->out_dt[l.input_layers[0]];
+            continue;
+        }
+        if (home[i].owner >= 0) continue;
+        e->out_tv[i] = make_tv(e->act_arena + buf_off[i], B, l.out_h, l.out_w, l.out_c, l.out_c, P, e->out_dt[i], 0);
+    }
+    // slices (owner buffers are allocated above since routes own their buffers)
+    for (int i = 0; i < nl; ++i) {
+        if (home[i].owner < 0) continue;
+        const Layer &l = net->layers[i];
+        const int r = home[i].owner;
+        e->out_tv[i] = make_tv(e->act_arena + buf_off[r], B, l.out_h, l.out_w, l.out_c, home[i].ldc, P, ADT, home[i].coff);
+    }
+    // single-input route aliases may point at slices that were only resolved now
+    for (int i = 0; i < nl; ++i) {
+        const Layer &l = net->layers[i];
+        if (has_nhwc_out(i) && l.type == YB_ROUTE && l.n == 1 && opt.fuse) {
+            e->out_tv[i] = e->out_tv[l.input_layers[0]];
+            e->out_dt[i] = e->out_dt[l.input_layers[0]];
+        }
+    }
+
+    // ---- final (host-visible) outputs ----------------------------------------------------------------
+    e->d_final.assign(nl, nullptr);
+    e->h_final.assign(nl, nullptr);
+    e->final_count.assign(nl, 0);
+    e->d_counts.assign(nl, nullptr);
+    e->counts_count.assign(nl, 0);
+    for (int i = 0; i < nl; ++i) {
+        const Layer &l = net->layers[i];
+        if (l.type == YB_YOLO || l.type == YB_REGION) {
+            e->final_count[i] = (size_t)l.outputs * B;
+            CUDA_OK(cudaMalloc(&e->d_final[i], e->final_count[i] * sizeof(float)));
+            CUDA_OK(cudaHostAlloc(&e->h_final[i], e->final_count[i] * sizeof(float), cudaHostAllocDefault));
+        }
+    }
+    {   // the reference returns the LAST layer's output; keep a host copy for it whatever its type
+        const int last = nl - 1;
+        const Layer &l = net->layers[last];
+        if (!e->d_final[last] && l.outputs > 0) {
+            e->final_count[last] = (size_t)l.outputs * B;
+            CUDA_OK(cudaMalloc(&e->d_final[last], e->final_count[last] * sizeof(float)));
+            CUDA_OK(cudaHostAlloc(&e->h_final[last], e->final_count[last] * sizeof(float), cudaHostAllocDefault));
+        }
+    }
+
+    // ---- weight arena ------------------------------------------------------------------------------
+    std::vector<ConvWeights> cw(nl);
+    std::vector<char> hostw;
+    auto reserve = [&](size_t bytes) { size_t off = align_up(hostw.size(), 1024); hostw.resize(off + bytes, 0); return off; };
+    std::vector<int> use_tc(nl, 0);
+    for (int i = 0; i < nl; ++i) {
+        const Layer &l = net->layers[i];
+        if (l.type != YB_CONVOLUTIONAL) continue;
+        const int v = conv_variant(i);
+        const int taps = l.size * l.size;
+        const int K = taps * l.c;
+        ConvWeights &w = cw[i];
+        w.bias = reserve(sizeof(float) * align_up(l.n, 64));
+        memcpy(&hostw[w.bias], l.biases.data(), sizeof(float) * l.n);
+        if (v == 0) {
+            const TV &tin = (i == 0) ? e->in0 : e->out_tv[i - 1];
+            const int in_dt = (i == 0) ? e->in0_dt : e->out_dt[i - 1];
+            const int odt = fused_into[i] >= 0 ? e->out_dt[fused_into[i]] : e->out_dt[i];
+            use_tc[i] = (ADT == DT_BF16 && in_dt == DT_BF16) ? tc_conv_supported(l, tin, odt == DT_BF16) : 0;
+            if (use_tc[i]) {
+                // bf16 [ldn][K], K ordered (ky, kx, c): the K-major B operand of the implicit GEMM
+                w.ldn = (int)align_up(l.n, 64);
+                w.w_bf16 = reserve(sizeof(__nv_bfloat16) * (size_t)w.ldn * K);
+                __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(&hostw[w.w_bf16]);
+                for (int f = 0; f < l.n; ++f)
+                    for (int c = 0; c < l.c; ++c)
+                        for (int t = 0; t < taps; ++t)
+                            dst[(size_t)f * K + (size_t)t * l.c + c] =
+                                __float2bfloat16_rn(l.weights[((size_t)f * l.c + c) * taps + t]);
+            } else {
+                // f32 [K][ldw], K ordered (ky, kx, c)
+                w.ldw = (int)align_up(l.n, 64);
+                w.w_f32 = reserve(sizeof(float) * (size_t)K * w.ldw);
+                float *dst = reinterpret_cast<float *>(&hostw[w.w_f32]);
+                for (int f = 0; f < l.n; ++f)
+                    for (int c = 0; c < l.c; ++c)
+                        for (int t = 0; t < taps; ++t)
+                            dst[((size_t)t * l.c + c) * w.ldw + f] = l.weights[((size_t)f * l.c + c) * taps + t];
+            }
+        } else if (v == 1) {
+            // sign bits [ldn][taps][CW]; bit = (w > 0) (binarize_weights additionally.c:113 + float_to_bit :1536)
+            const int CW = (l.c + 31) / 32;
+            w.ldn = (int)align_up(l.n, 64);
+            w.cpad = CW * 32;
+            w.w_bits = reserve(sizeof(uint32_t) * (size_t)w.ldn * taps * CW);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(&hostw[w.w_bits]);
+            for (int f = 0; f < l.n; ++f)
+                for (int c = 0; c < l.c; ++c)
+                    for (int t = 0; t < taps; ++t)
+                        if (l.weights[((size_t)f * l.c + c) * taps + t] > 0)
+                            dst[((size_t)f * taps + t) * CW + c / 32] |= 1u << (c & 31);
+            w.mean = reserve(sizeof(float) * align_up(l.n, 64));
+            memcpy(&hostw[w.mean], l.mean_arr.data(), sizeof(float) * l.n);
+        } else {
+            // s8 [ldn][taps][cpad], zero channel padding
+            w.cpad = side_ld[i];
+            w.ldn = (int)align_up(l.n, 64);
+            w.w_s8 = reserve((size_t)w.ldn * taps * w.cpad);
+            int8_t *dst = reinterpret_cast<int8_t *>(&hostw[w.w_s8]);
+            for (int f = 0; f < l.n; ++f)
+                for (int c = 0; c < l.c; ++c)
+                    for (int t = 0; t < taps; ++t)
+                        dst[((size_t)f * taps + t) * w.cpad + c] = l.weights_int8[((size_t)f * l.c + c) * taps + t];
+        }
+    }
+    e->w_bytes = align_up(std::max<size_t>(hostw.size(), 1024), 1024);
+    CUDA_OK(cudaMalloc(&e->w_arena, e->w_bytes));
+    if (opt.upload) CUDA_OK(cudaMemcpyAsync(e->w_arena, hostw.data(), hostw.size(), cudaMemcpyHostToDevice, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));   // hostw goes out of scope below
+
+    // ---- input staging -----------------------------------------------------------------------------
+    e->input_count = (size_t)B * net->c * net->h * net->w;
+    CUDA_OK(cudaMalloc(&e->d_input, e->input_count * sizeof(float)));
+
+    // ---- op list -----------------------------------------------------------------------------------
+    Engine *E = e.get();
+    {
+        TV in0 = e->in0;
+        const int dt = e->in0_dt;
+        e->ops.push_back(Op{OP_INPUT, -1, nullptr});   // launched specially (input pointer varies per call)
+        (void)in0; (void)dt;
+    }
+    for (int i = 0; i < nl; ++i) {
+        const Layer &l = net->layers[i];
+        const TV tin = (i == 0) ? e->in0 : e->out_tv[i - 1];
+        const int in_dt = (i == 0) ? e->in0_dt : e->out_dt[i - 1];
+        const bool prev_ok = (i == 0) || e->out_tv[i - 1].base != nullptr;
+        auto need_prev = [&]() {
+            if (!prev_ok) fatal_throw("engine: layer " + std::to_string(i) + " has no image input");
+        };
+        switch (l.type) {
+        case YB_CONVOLUTIONAL: {
+            need_prev();
+            const int v = conv_variant(i);
+            const int tgt = fused_into[i] >= 0 ? fused_into[i] : i;
+            const TV tout = e->out_tv[tgt];
+            const int odt = e->out_dt[tgt];
+            if (!tout.base) fatal_throw("engine: conv output not placed");
+            if (tin.C != l.c || tin.H != l.h || tin.W != l.w) fatal_throw("engine: conv input shape mismatch");
+            const long M = (long)B * l.out_h * l.out_w;
+            if (v == 0) {
+                TV res{}; int rdt = DT_F32; int act2 = ACT_LINEAR;
+                if (fused_into[i] >= 0) {
+                    const Layer &s = net->layers[tgt];
+                    res = e->out_tv[s.index];
+                    rdt = e->out_dt[s.index];
+                    act2 = s.activation;
+                    if (!res.base) fatal_throw("engine: shortcut source not placed");
+                }
+                if (use_tc[i]) {
+                    void *plan = tc_make_plan(l, tin, tout, odt == DT_BF16, res, rdt == DT_BF16, act2,
+                                              e->w_arena + cw[i].w_bf16, cw[i].ldn,
+                                              reinterpret_cast<const float *>(e->w_arena + cw[i].bias));
+                    e->tc_plans.push_back(plan);
+                    e->ops.push_back(Op{OP_CONV_TC, i, [plan](cudaStream_t s) { tc_launch(plan, s); }});
+                } else {
+                    ConvP p{};
+                    p.in = tin; p.out = tout; p.res = res;
+                    p.w = e->w_arena + cw[i].w_f32;
+                    p.bias = reinterpret_cast<const float *>(e->w_arena + cw[i].bias);
+                    p.n = l.n; p.ldw = cw[i].ldw; p.size = l.size; p.stride = l.stride; p.pad = l.pad;
+                    p.act = l.activation; p.act2 = act2; p.K = l.size * l.size * l.c; p.M = M;
+                    dim3 grid((unsigned)((M + 63) / 64), (unsigned)((l.n + 63) / 64));
+                    const int key = in_dt * 4 + odt * 2 + rdt;
+                    e->ops.push_back(Op{OP_CONV_SIMT, i, [p, grid, key](cudaStream_t s) {
+                        switch (key) {
+                        case 0: k_conv_simt<float, float, float><<<grid, 256, 0, s>>>(p); break;
+                        case 1: k_conv_simt<float, float, __nv_bfloat16><<<grid, 256, 0, s>>>(p); break;
+                        case 2: k_conv_simt<float, __nv_bfloat16, float><<<grid, 256, 0, s>>>(p); break;
+                        case 3: k_conv_simt<float, __nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, s>>>(p); break;
+                        case 4: k_conv_simt<__nv_bfloat16, float, float><<<grid, 256, 0, s>>>(p); break;
+                        case 5: k_conv_simt<__nv_bfloat16, float, __nv_bfloat16><<<grid, 256, 0, s>>>(p); break;
+                        case 6: k_conv_simt<__nv_bfloat16, __nv_bfloat16, float><<<grid, 256, 0, s>>>(p); break;
+                        default: k_conv_simt<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, s>>>(p); break;
+                        }
+                    }});
+                }
+            } else if (v == 1) {
+                if (in_dt != DT_F32 || odt != DT_F32) fatal_throw("engine: xnor path needs f32 activations");
+                const int CW = side_ld[i];
+                TV bits = make_tv(e->act_arena + side_off[i], B, l.h, l.w, CW, CW, P, DT_BITS, 0);
+                {
+                    const long total = (long)B * l.h * l.w * CW * 32;
+                    const int g = grid_for(total);
+                    e->ops.push_back(Op{OP_BINARIZE, i, [tin, bits, g](cudaStream_t s) { k_binarize<float><<<g, 256, 0, s>>>(tin, bits); }});
+                }
+                XnorP p{};
+                p.bits = bits; p.out = tout;
+                p.w = reinterpret_cast<const uint32_t *>(e->w_arena + cw[i].w_bits);
+                p.mean = reinterpret_cast<const float *>(e->w_arena + cw[i].mean);
+                p.bias = reinterpret_cast<const float *>(e->w_arena + cw[i].bias);
+                p.n = l.n; p.size = l.size; p.pad = l.pad; p.K = l.size * l.size * l.c;
+                p.padbits = (CW * 32 - l.c) * l.size * l.size;
+                p.act = l.activation; p.M = M; p.counts = nullptr;
+                if (opt.keep_counts) {
+                    e->counts_count[i] = (size_t)B * l.n * l.out_h * l.out_w;
+                    CUDA_OK(cudaMalloc(&e->d_counts[i], e->counts_count[i] * sizeof(int32_t)));
+                    p.counts = e->d_counts[i];
+                }
+                dim3 grid((unsigned)((M + 63) / 64), (unsigned)((l.n + 63) / 64));
+                e->ops.push_back(Op{OP_CONV_XNOR, i, [p, grid](cudaStream_t s) { k_conv_xnor<<<grid, 256, 0, s>>>(p); }});
+            } else {
+                if (in_dt != DT_F32 || odt != DT_F32) fatal_throw("engine: int8 path needs f32 activations");
+                const int cpad = side_ld[i];
+                TV q = make_tv(e->act_arena + side_off[i], B, l.h, l.w, l.c, cpad, P, DT_S8, 0);
+                const float mult = l.input_quant_multipler;
+                {
+                    const long total = (long)B * l.h * l.w * (cpad / 4);
+                    const int g = grid_for(total);
+                    e->ops.push_back(Op{OP_QUANTIZE, i, [tin, q, mult, g](cudaStream_t s) { k_quantize<float><<<g, 256, 0, s>>>(tin, q, mult); }});
+                }
+                Int8P p{};
+                p.q = q; p.out = tout;
+                p.w = reinterpret_cast<const uint32_t *>(e->w_arena + cw[i].w_s8);
+                p.bias = reinterpret_cast<const float *>(e->w_arena + cw[i].bias);
+                p.alpha1 = 32 / (l.input_quant_multipler * l.weights_quant_multipler);   // ALPHA1, ..._quantized.c:598
+                p.n = l.n; p.size = l.size; p.stride = l.stride; p.pad = l.pad; p.act = l.activation;
+                p.CW = cpad / 4; p.M = M; p.acc_out = nullptr;
+                if (opt.keep_counts) {
+                    e->counts_count[i] = (size_t)B * l.n * l.out_h * l.out_w;
+                    CUDA_OK(cudaMalloc(&e->d_counts[i], e->counts_count[i] * sizeof(int32_t)));
+                    p.acc_out = e->d_counts[i];
+                }
+                dim3 grid((unsigned)((M + 63) / 64), (unsigned)((l.n + 63) / 64));
+                e->ops.push_back(Op{OP_CONV_INT8, i, [p, grid](cudaStream_t s) { k_conv_int8_simt<<<grid, 256, 0, s>>>(p); }});
+            }
+            break;
+        }
+        case YB_MAXPOOL: {
+            need_prev();
+            const TV tout = e->out_tv[i];
+            const int size = l.size, stride = l.stride, pad = l.pad;
+            const int g = grid_for((long)B * l.out_h * l.out_w * l.out_c);
+            const int dt = in_dt;
+            e->ops.push_back(Op{OP_MAXPOOL, i, [tin, tout, size, stride, pad, g, dt](cudaStream_t s) {
+                if (dt == DT_F32) k_maxpool<float><<<g, 256, 0, s>>>(tin, tout, size, stride, pad);
+                else k_maxpool<__nv_bfloat16><<<g, 256, 0, s>>>(tin, tout, size, stride, pad);
+            }});
+            break;
+        }
+        case YB_UPSAMPLE: {
+            need_prev();
+            if (l.reverse) fatal_throw("engine: reverse upsample (downsample) is not supported");
+            const TV tout = e->out_tv[i];
+            const int stride = l.stride; const float scale = l.scale;
+            const int g = grid_for((long)B * l.out_h * l.out_w * l.out_c);
+            const int dt = in_dt;
+            e->ops.push_back(Op{OP_UPSAMPLE, i, [tin, tout, stride, scale, g, dt](cudaStream_t s) {
+                if (dt == DT_F32) k_upsample<float><<<g, 256, 0, s>>>(tin, tout, stride, scale);
+                else k_upsample<__nv_bfloat16><<<g, 256, 0, s>>>(tin, tout, stride, scale);
+            }});
+            break;
+        }
+        case YB_SHORTCUT: {
+            if (is_fused_sc[i]) break;
+            need_prev();
+            const TV tout = e->out_tv[i];
+            const TV from = e->out_tv[l.index];
+            if (!from.base) fatal_throw("engine: shortcut source not placed");
+            if (e->out_dt[l.index] != in_dt) fatal_throw("engine: shortcut dtype mismatch");
+            // shortcut_cpu(batch, w1=l.w, h1=l.h, c1=l.c (from), add, w2=l.out_w, ...): yolov2_forward_network.c:410
+            int stride = l.w / l.out_w, sample = l.out_w / l.w;
+            if (stride < 1) stride = 1;
+            if (sample < 1) sample = 1;
+            const int minw = std::min(l.w, l.out_w), minh = std::min(l.h, l.out_h), minc = std::min(l.c, l.out_c);
+            const int act = l.activation;
+            const int g = grid_for((long)B * l.out_h * l.out_w * l.out_c);
+            const int dt = in_dt;
+            e->ops.push_back(Op{OP_SHORTCUT, i, [=](cudaStream_t s) {
+                if (dt == DT_F32) k_shortcut<float><<<g, 256, 0, s>>>(tin, from, tout, stride, sample, minw, minh, minc, act);
+                else k_shortcut<__nv_bfloat16><<<g, 256, 0, s>>>(tin, from, tout, stride, sample, minw, minh, minc, act);
+            }});
+            break;
+        }
+        case YB_ROUTE: {
+            if (!has_nhwc_out(i)) fatal_throw("engine: route over layers of different spatial size is not supported");
+            if (l.n == 1 && opt.fuse) break;   // alias
+            int off = 0;
+            for (int k = 0; k < l.n; ++k) {
+                const int j = l.input_layers[k];
+                const Layer &src = net->layers[j];
+                if (!(home[j].owner == i)) {
+                    const TV tsrc = e->out_tv[j];
+                    if (!tsrc.base) fatal_throw("engine: route source not placed");
+                    if (e->out_dt[j] != e->out_dt[i]) fatal_throw("engine: route dtype mismatch");
+                    TV slice = e->out_tv[i];
+                    slice.base += (size_t)off * dt_size(e->out_dt[i]);
+                    slice.C = src.out_c;
+                    const int g = grid_for((long)B * src.out_h * src.out_w * src.out_c);
+                    const int dt = e->out_dt[i];
+                    e->ops.push_back(Op{OP_ROUTE_COPY, i, [tsrc, slice, g, dt](cudaStream_t s) {
+                        if (dt == DT_F32) k_copy_channels<float><<<g, 256, 0, s>>>(tsrc, slice);
+                        else k_copy_channels<__nv_bfloat16><<<g, 256, 0, s>>>(tsrc, slice);
+                    }});
+                }
+                off += src.out_c;
+            }
+            break;
+        }
+        case YB_REORG: {
+            need_prev();
+            if (l.reverse) fatal_throw("engine: reverse reorg is not supported");
+            const TV tout = e->out_tv[i];
+            const int stride = l.stride;
+            const int g = grid_for((long)B * l.out_h * l.out_w * l.out_c);
+            const int dt = in_dt;
+            e->ops.push_back(Op{OP_REORG, i, [tin, tout, stride, g, dt](cudaStream_t s) {
+                if (dt == DT_F32) k_reorg<float><<<g, 256, 0, s>>>(tin, tout, stride);
+                else k_reorg<__nv_bfloat16><<<g, 256, 0, s>>>(tin, tout, stride);
+            }});
+            break;
+        }
+        case YB_YOLO: {
+            need_prev();
+            float *dst = e->d_final[i];
+            const int classes = l.classes;
+            const int g = grid_for((long)B * l.outputs);
+            const int dt = in_dt;
+            e->ops.push_back(Op{OP_YOLO, i, [tin, dst, classes, g, dt](cudaStream_t s) {
+                if (dt == DT_F32) k_yolo<float><<<g, 256, 0, s>>>(tin, dst, classes);
+                else k_yolo<__nv_bfloat16><<<g, 256, 0, s>>>(tin, dst, classes);
+            }});
+            break;
+        }
+        case YB_REGION: {
+            need_prev();
+            float *dst = e->d_final[i];
+            const int n = l.n, classes = l.classes, coords = l.coords, softmax = l.softmax;
+            const int g = grid_for((long)B * l.h * l.w * l.n);
+            const int dt = in_dt;
+            e->ops.push_back(Op{OP_REGION, i, [tin, dst, n, classes, coords, softmax, g, dt](cudaStream_t s) {
+                if (dt == DT_F32) k_region<float><<<g, 256, 0, s>>>(tin, dst, n, classes, coords, softmax);
+                else k_region<__nv_bfloat16><<<g, 256, 0, s>>>(tin, dst, n, classes, coords, softmax);
+            }});
+            break;
+        }
+        default:
+            break;
+        }
+    }
+    // last layer that is not yolo/region: keep an NCHW f32 copy as "the network output"
+    {
+        const int last = nl - 1;
+        const Layer &l = net->layers[last];
+        if (l.type != YB_YOLO && l.type != YB_REGION && e->d_final[last]) {
+            int src = last;
+            if (fused_into[last] >= 0) src = fused_into[last];
+            const TV t = e->out_tv[src];
+            if (t.base) {
+                float *dst = e->d_final[last];
+                const int dt = e->out_dt[src];
+                const int g = grid_for((long)B * l.outputs);
+                e->ops.push_back(Op{OP_YOLO, last, [t, dst, g, dt](cudaStream_t s) {
+                    if (dt == DT_F32) k_nhwc_to_nchw_f32<float><<<g, 256, 0, s>>>(t, dst);
+                    else k_nhwc_to_nchw_f32<__nv_bfloat16><<<g, 256, 0, s>>>(t, dst);
+                }});
+            }
+        }
+    }
+    (void)E;
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    CUDA_OK(cudaGetLastError());
+    return e;
+}
+
+static void launch_input(Engine *e, const float *d_in, cudaStream_t s) {
+    const TV in0 = e->in0;
+    const int g = grid_for((long)in0.N * in0.H * in0.W);
+    if (e->in0_dt == DT_F32) k_input_nchw_to_nhwc<float><<<g, 256, 0, s>>>(d_in, in0);
+    else k_input_nchw_to_nhwc<__nv_bfloat16><<<g, 256, 0, s>>>(d_in, in0);
+}
+
+void engine_upload_input(Engine *e, const float *host_input, void *stream) {
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    CUDA_OK(cudaSetDevice(e->opt.device));
+    CUDA_OK(cudaMemcpyAsync(e->d_input, host_input, e->input_count * sizeof(float), cudaMemcpyHostToDevice, s));
+}
+
+void *engine_stream(Engine *e) { return e->stream; }
+
+void engine_forward(Engine *e, const void *d_input, void *stream) {
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    CUDA_OK(cudaSetDevice(e->opt.device));   // thread identity may change per call (threading)
+    const float *din = d_input ? reinterpret_cast<const float *>(d_input) : e->d_input;
+    launch_input(e, din, s);
+    if (!e->graph_exec && !e->graph_failed) {
+        // capture everything after the input conversion once
+        cudaGraph_t graph = nullptr;
+        cudaError_t st = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+        if (st == cudaSuccess) {
+            for (size_t k = 1; k < e->ops.size(); ++k) e->ops[k].launch(s);
+            st = cudaStreamEndCapture(s, &graph);
+        }
+        if (st == cudaSuccess && graph) {
+            st = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+        }
+        if (st != cudaSuccess || !e->graph_exec) {
+            e->graph_failed = true;
+            e->graph_exec = nullptr;
+            cudaGetLastError();
+        }
+    }
+    if (e->graph_exec) {
+        CUDA_OK(cudaGraphLaunch(e->graph_exec, s));
+    } else {
+        for (size_t k = 1; k < e->ops.size(); ++k) e->ops[k].launch(s);
+    }
+    CUDA_OK(cudaGetLastError());
+}
+
+void engine_download_outputs(Engine *e, Network *net, void *stream) {
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    CUDA_OK(cudaSetDevice(e->opt.device));
+    for (size_t i = 0; i < e->d_final.size(); ++i) {
+        if (!e->d_final[i]) continue;
+        CUDA_OK(cudaMemcpyAsync(e->h_final[i], e->d_final[i], e->final_count[i] * sizeof(float), cudaMemcpyDeviceToHost, s));
+        net->layers[i].output = e->h_final[i];
+        net->layers[i].output_count = e->final_count[i];
+    }
+    CUDA_OK(cudaStreamSynchronize(s));
+}
+
+void engine_fetch_layer(Engine *e, Network *net, int layer, float *dst) {
+    CUDA_OK(cudaSetDevice(e->opt.device));
+    const Layer &l = net->layers[layer];
+    const size_t count = (size_t)l.outputs * e->batch;
+    if (e->d_final[layer] && (l.type == YB_YOLO || l.type == YB_REGION)) {
+        CUDA_OK(cudaMemcpy(dst, e->d_final[layer], count * sizeof(float), cudaMemcpyDeviceToHost));
+        return;
+    }
+    const TV t = e->out_tv[layer];
+    if (!t.base) fatal_throw("fetch_layer: layer " + std::to_string(layer) + " has no materialised output "
+                             "(fused or aliased away; build the engine with fusion off)");
+    float *tmp = nullptr;
+    CUDA_OK(cudaMalloc(&tmp, count * sizeof(float)));
+    const int g = grid_for((long)count);
+    if (e->out_dt[layer] == DT_F32) k_nhwc_to_nchw_f32<float><<<g, 256, 0, e->stream>>>(t, tmp);
+    else k_nhwc_to_nchw_f32<__nv_bfloat16><<<g, 256, 0, e->stream>>>(t, tmp);
+    CUDA_OK(cudaMemcpyAsync(dst, tmp, count * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    cudaFree(tmp);
+}
+
+int engine_fetch_counts(Engine *e, int layer, int32_t *dst, size_t count) {
+    if (layer < 0 || layer >= (int)e->d_counts.size() || !e->d_counts[layer]) return -1;
+    if (count < e->counts_count[layer]) return -2;
+    CUDA_OK(cudaSetDevice(e->opt.device));
+    CUDA_OK(cudaMemcpy(dst, e->d_counts[layer], e->counts_count[layer] * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return (int)e->counts_count[layer];
+}
+
+void engine_weight_arena(Engine *e, void **ptr, size_t *bytes) { *ptr = e->w_arena; *bytes = e->w_bytes; }
+int engine_num_launches(Engine *e) { return (int)e->ops.size(); }
+
+int engine_profile(Engine *e, const void *d_input, int *layer_idx, int *op_kind, float *ms, int max) {
+    CUDA_OK(cudaSetDevice(e->opt.device));
+    cudaStream_t s = e->stream;
+    const float *din = d_input ? reinterpret_cast<const float *>(d_input) : e->d_input;
+    const int n = (int)e->ops.size();
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto &x : ev) CUDA_OK(cudaEventCreate(&x));
+    for (int rep = 0; rep < 2; ++rep) {   // second pass is the measured one
+        CUDA_OK(cudaEventRecord(ev[0], s));
+        for (int k = 0; k < n; ++k) {
+            if (k == 0) launch_input(e, din, s);
+            else e->ops[k].launch(s);
+            CUDA_OK(cudaEventRecord(ev[k + 1], s));
+        }
+        CUDA_OK(cudaStreamSynchronize(s));
+    }
+    for (int k = 0; k < n && k < max; ++k) {
+        layer_idx[k] = e->ops[k].layer;
+        op_kind[k] = e->ops[k].kind;
+        CUDA_OK(cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]));
+    }
+    for (auto &x : ev) cudaEventDestroy(x);
+    return n;
+}
+
+}  // namespace yb
+
+extern "C" void *yb_alloc_pinned(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void yb_free_pinned(void *p) { if (p) cudaFreeHost(p); }

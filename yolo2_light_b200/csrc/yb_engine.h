@@ -1,0 +1,45 @@
+// yb_engine.h -- device-side execution plan of one prepared network ("engine"): compiled once per
+// (network, rule) from the host model, then replayed as a CUDA graph.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "yb_model.h"
+
+namespace yb {
+
+enum OpKind {
+    OP_INPUT = 0, OP_CONV_SIMT = 1, OP_CONV_TC = 2, OP_BINARIZE = 3, OP_CONV_XNOR = 4, OP_QUANTIZE = 5,
+    OP_CONV_INT8 = 6, OP_MAXPOOL = 7, OP_UPSAMPLE = 8, OP_SHORTCUT = 9, OP_ROUTE_COPY = 10, OP_REORG = 11,
+    OP_YOLO = 12, OP_REGION = 13, OP_CONV_TC_I8 = 14
+};
+
+struct EngineOptions {
+    int device = 0;
+    int precision = YB_PREC_BF16_TC;
+    bool qrule = false;        // yolov2_forward_network_q layer rule
+    bool fuse = true;          // conv + shortcut fusion, route aliasing
+    bool upload = true;        // upload the weight arena (false on non-root ranks before the broadcast)
+    int q_index_offset = 0;    // added to the layer index in the `i >= 1` INT8 rule (single-layer runs)
+    bool keep_counts = false;  // keep raw XNOR popcounts / INT8 accumulators (tests)
+};
+
+struct Engine;
+std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt);
+// d_input == nullptr: use the engine's staging buffer (filled by engine_upload_input)
+void engine_upload_input(Engine *e, const float *host_input, void *stream);
+void engine_forward(Engine *e, const void *d_input, void *stream);
+void engine_download_outputs(Engine *e, Network *net, void *stream);   // async D2H into pinned, then sync
+void engine_fetch_layer(Engine *e, Network *net, int layer, float *dst);
+int engine_fetch_counts(Engine *e, int layer, int32_t *dst, size_t count);
+void engine_weight_arena(Engine *e, void **ptr, size_t *bytes);
+int engine_num_launches(Engine *e);
+int engine_profile(Engine *e, const void *d_input, int *layer_idx, int *op_kind, float *ms, int max);
+void *engine_stream(Engine *e);
+const char *op_kind_name(int k);
+
+}  // namespace yb

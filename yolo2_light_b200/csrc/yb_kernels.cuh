@@ -1,0 +1,612 @@
+// yb_kernels.cuh -- CUDA-core (SIMT) kernels of the engine: layout converters, the generic FP32 / XNOR / INT8
+// convolutions and all small layers.  sm_100a only.  The tensor-core (tcgen05) convolutions live in
+// yb_conv_tc.cuh.
+//
+// Device activation layout ("padded NHWC"): element (n, y, x, c) of a tensor with logical dims N,H,W,C lives at
+//     base + (((n*(H+2P) + y+P) * (W+2P) + x+P) * ldc + c) * sizeof(T)
+// with a P=1 pixel border that is zero-filled once at allocation and never written -- 3x3/pad-1 convolutions
+// (and their TMA loads) read the border instead of bounds-checking.  ldc >= C lets a tensor be a channel slice
+// of a wider concat buffer (route layers become aliasing).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace yb {
+
+struct TV {            // tensor view (POD, passed by value to kernels)
+    char *base;        // address of channel 0 of padded pixel (n=0, y=-P, x=-P)
+    int N, H, W, C;
+    int ldc;           // elements per pixel in the underlying buffer
+    int P;             // border
+    int Hp, Wp;        // H+2P, W+2P
+};
+
+template <typename T>
+__device__ __forceinline__ T *tv_px(const TV &t, int n, int y, int x) {
+    return reinterpret_cast<T *>(t.base) + ((size_t)(n * t.Hp + y + t.P) * t.Wp + (x + t.P)) * (size_t)t.ldc;
+}
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+enum { ACT_LOGISTIC = 0, ACT_RELU = 1, ACT_LINEAR = 3, ACT_LEAKY = 7 };
+
+// activate(), reference additionally.h:126-157 (scalar build): leaky = x>0 ? x : (float)(.1 * (double)x),
+// logistic = (float)(1./(1.+exp(-x))) in double.  Used by the "exact" paths.
+__device__ __forceinline__ float act_exact(float x, int a) {
+    if (a == ACT_LEAKY) return (x > 0.f) ? x : (float)(0.1 * (double)x);
+    if (a == ACT_LINEAR) return x;
+    if (a == ACT_LOGISTIC) return (float)(1.0 / (1.0 + exp(-(double)x)));
+    if (a == ACT_RELU) return x * (x > 0.f);
+    return x;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// input: NCHW f32 (host contract, reference additionally.c:3093-3103) -> padded NHWC
+// ------------------------------------------------------------------------------------------------------
+template <typename TOut>
+__global__ void k_input_nchw_to_nhwc(const float *__restrict__ in, TV out) {
+    const long total = (long)out.N * out.H * out.W;
+    for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < total; p += (long)gridDim.x * blockDim.x) {
+        const int x = (int)(p % out.W);
+        const int y = (int)((p / out.W) % out.H);
+        const int n = (int)(p / ((long)out.W * out.H));
+        TOut *o = tv_px<TOut>(out, n, y, x);
+        const float *src = in + ((size_t)n * out.C * out.H + y) * out.W + x;
+        for (int c = 0; c < out.C; ++c) o[c] = from_f32<TOut>(src[(size_t)c * out.H * out.W]);
+    }
+}
+
+// any padded-NHWC activation -> NCHW f32 (diagnostic fetch)
+template <typename TIn>
+__global__ void k_nhwc_to_nchw_f32(TV in, float *__restrict__ out) {
+    const long total = (long)in.N * in.C * in.H * in.W;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % in.W);
+        const int y = (int)((i / in.W) % in.H);
+        const int c = (int)((i / ((long)in.W * in.H)) % in.C);
+        const int n = (int)(i / ((long)in.W * in.H * in.C));
+        out[i] = to_f32(tv_px<TIn>(in, n, y, x)[c]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// generic FP32 convolution on CUDA cores (implicit GEMM, 64 pixels x 64 filters per CTA, 4x4 per thread).
+// Semantics: forward_convolutional_layer_cpu FP32 branch (reference yolov2_forward_network.c:204-261):
+// out = act(sum_{c,ky,kx} w*in + bias) with zero padding; optional fused shortcut (reference :443-449):
+// out = act2(act(..) + residual).  Used for: validation precision (YB_PREC_FP32), the FP32 layers of
+// XNOR / INT8 networks, the 3-channel stem, and any shape the tensor-core kernel does not take.
+// Weights: [K][ldw] f32, K ordered (ky, kx, c), ldw = filters rounded up to 64.
+// ------------------------------------------------------------------------------------------------------
+struct ConvP {
+    TV in, out, res;           // res.base == nullptr: no residual
+    const void *w;
+    const float *bias;
+    int n;                     // filters
+    int ldw;
+    int size, stride, pad;
+    int act, act2;
+    int K;                     // size*size*C
+    long M;                    // N*out_h*out_w
+};
+
+template <typename TIn, typename TOut, typename TRes>
+__global__ void __launch_bounds__(256) k_conv_simt(ConvP p) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const long m0 = (long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const int OH = p.out.H, OW = p.out.W, C = p.in.C;
+
+    // A-load role: thread -> (pixel tid/4, 4 consecutive k starting at (tid%4)*4)
+    const int lp = tid >> 2, lk = (tid & 3) * 4;
+    const long lm = m0 + lp;
+    const bool lvalid = lm < p.M;
+    int ln = 0, liy0 = 0, lix0 = 0;
+    if (lvalid) {
+        const int ox = (int)(lm % OW);
+        const int oy = (int)((lm / OW) % OH);
+        ln = (int)(lm / ((long)OW * OH));
+        liy0 = oy * p.stride - p.pad;
+        lix0 = ox * p.stride - p.pad;
+    }
+    // B-load role: thread -> (k row tid/16, 4 consecutive filters (tid%16)*4)
+    const int bk = tid >> 4, bn = (tid & 15) * 4;
+    const float *wptr = reinterpret_cast<const float *>(p.w);
+
+    const int tx = tid & 15, ty = tid >> 4;   // compute role: pixels ty*4.., filters tx*4..
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < p.K; k0 += BK) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = k0 + lk + q;
+            float v = 0.f;
+            if (lvalid && k < p.K) {
+                const int tap = k / C, ch = k - tap * C;
+                const int ky = tap / p.size, kx = tap - ky * p.size;
+                const int iy = liy0 + ky, ix = lix0 + kx;
+                if (iy >= 0 && iy < p.in.H && ix >= 0 && ix < p.in.W) v = to_f32(tv_px<TIn>(p.in, ln, iy, ix)[ch]);
+            }
+            As[lk + q][lp] = v;
+        }
+        {
+            const int k = k0 + bk;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < p.K) v = *reinterpret_cast<const float4 *>(wptr + (size_t)k * p.ldw + n0 + bn);
+            Bs[bk][bn + 0] = v.x; Bs[bk][bn + 1] = v.y; Bs[bk][bn + 2] = v.z; Bs[bk][bn + 3] = v.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long m = m0 + ty * 4 + i;
+        if (m >= p.M) continue;
+        const int ox = (int)(m % OW);
+        const int oy = (int)((m / OW) % OH);
+        const int n = (int)(m / ((long)OW * OH));
+        TOut *o = tv_px<TOut>(p.out, n, oy, ox);
+        const TRes *r = p.res.base ? tv_px<TRes>(p.res, n, oy, ox) : nullptr;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int f = n0 + tx * 4 + j;
+            if (f >= p.n) continue;
+            float v = act_exact(acc[i][j] + p.bias[f], p.act);
+            if (r) v = act_exact(v + to_f32(r[f]), p.act2);
+            o[f] = from_f32<TOut>(v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// BIT1-XNOR path (reference yolov2_forward_network.c:116-203).
+// k_binarize: f32 activation -> 1 bit per channel, bit = (x > 0), 32 channels per word, padded NHWC with a
+// zero (== -1, F9) border.  One warp per (pixel, word): coalesced read + __ballot_sync.
+// ------------------------------------------------------------------------------------------------------
+template <typename TIn>
+__global__ void k_binarize(TV in, TV bits /* C = words per pixel */) {
+    const int lane = threadIdx.x & 31;
+    const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    const int CW = bits.C;
+    const long total = (long)in.N * in.H * in.W * CW;
+    for (long i = warp; i < total; i += nwarps) {
+        const int wd = (int)(i % CW);
+        const long pxl = i / CW;
+        const int x = (int)(pxl % in.W);
+        const int y = (int)((pxl / in.W) % in.H);
+        const int n = (int)(pxl / ((long)in.W * in.H));
+        const int c = wd * 32 + lane;
+        float v = 0.f;
+        if (c < in.C) v = to_f32(tv_px<TIn>(in, n, y, x)[c]);
+        const unsigned m = __ballot_sync(0xffffffffu, v > 0.f);
+        if (lane == 0) tv_px<uint32_t>(bits, n, y, x)[wd] = m;
+    }
+}
+
+// XNOR bit-GEMM convolution, 3x3 / stride 1 / pad 1: count = sum_taps popc(~(a ^ w)) - (pad bits), then
+// out = act((2*count - K) * mean[f] + bias[f]) evaluated in the reference's float op order
+// (additionally.c:1531, yolov2_forward_network.c:243-261).  64 pixels x 64 filters per CTA, 4x4 per thread,
+// K streamed through shared memory in 8-word slices with 128-bit loads.
+struct XnorP {
+    TV bits;                  // input bits, C = words per pixel (CW)
+    TV out;                   // f32
+    const uint32_t *w;        // [ldn filters][9 taps][CW] sign bits
+    const float *mean, *bias;
+    int n, size, pad;
+    int K;                    // true bit count size*size*C
+    int padbits;              // (CW*32 - C) * size*size
+    int act;
+    long M;
+    int32_t *counts;          // optional raw popcounts, NCHW (tests)
+};
+
+static __global__ void __launch_bounds__(256) k_conv_xnor(XnorP p) {
+    constexpr int BM = 64, BN = 64, BKW = 8;
+    __shared__ uint32_t As[BKW][BM + 1];
+    __shared__ uint32_t Bs[BKW][BN + 1];
+    const int tid = threadIdx.x;
+    const long m0 = (long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const int H = p.out.H, W = p.out.W, CW = p.bits.C;
+    const int taps = p.size * p.size;
+    const int KW = taps * CW;
+
+    // loader roles: 64 rows x 8 words = 512 words per operand, 2 per thread
+    const int lr = tid >> 2, lw = (tid & 3) * 2;
+    const long lm = m0 + lr;
+    const bool lvalid = lm < p.M;
+    int ln = 0, ly = 0, lx = 0;
+    if (lvalid) {
+        lx = (int)(lm % W);
+        ly = (int)((lm / W) % H);
+        ln = (int)(lm / ((long)W * H));
+    }
+    const int tx = tid & 15, ty = tid >> 4;
+    int acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0;
+
+    for (int k0 = 0; k0 < KW; k0 += BKW) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int k = k0 + lw + q;
+            uint32_t a = 0, b = 0;
+            if (k < KW) {
+                const int tap = k / CW, wd = k - tap * CW;
+                if (lvalid) {
+                    const int ky = tap / p.size, kx = tap - ky * p.size;
+                    const int iy = ly + ky - p.pad, ix = lx + kx - p.pad;
+                    // out-of-image taps read 0-bits (== -1): border for pad<=1, explicit otherwise
+                    if (iy >= -p.bits.P && iy < H + p.bits.P && ix >= -p.bits.P && ix < W + p.bits.P)
+                        a = tv_px<uint32_t>(p.bits, ln, iy, ix)[wd];
+                }
+                const int f = n0 + lr;
+                b = p.w[(size_t)f * KW + k];
+            } else {
+                a = 0; b = 0xffffffffu;   // a ^ b = all ones -> xnor contributes 0
+            }
+            As[lw + q][lr] = a;
+            Bs[lw + q][lr] = b;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BKW; ++kk) {
+            uint32_t a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] += __popc(~(a[i] ^ b[j]));
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long m = m0 + ty * 4 + i;
+        if (m >= p.M) continue;
+        const int x = (int)(m % W);
+        const int y = (int)((m / W) % H);
+        const int n = (int)(m / ((long)W * H));
+        float *o = tv_px<float>(p.out, n, y, x);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int f = n0 + tx * 4 + j;
+            if (f >= p.n) continue;
+            const int count = acc[i][j] - p.padbits;
+            if (p.counts) p.counts[(((size_t)n * p.n + f) * H + y) * W + x] = count;
+            float v = __fmul_rn((float)(2 * count - p.K), p.mean[f]);   // no fma contraction: one mul, one add
+            v = __fadd_rn(v, p.bias[f]);
+            o[f] = act_exact(v, p.act);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// INT8 path (reference yolov2_forward_network_quantized.c:527-631).
+// k_quantize: xq = clamp(+-127, (int16_t)(x * input_mult)) with x86 float->int16 semantics (cvttss2si, low
+// 16 bits, indefinite -> 0).  Output s8 padded NHWC, channels padded with zeros to ldc.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int quant_i8(float x, float mult) {
+    const float v = __fmul_rn(x, mult);
+    int i;
+    if (!(v > -2147483648.0f && v < 2147483648.0f)) i = (int)0x80000000;
+    else i = __float2int_rz(v);
+    int s = (int)(short)(i & 0xffff);
+    if (s > 127) s = 127;
+    if (s < -127) s = -127;
+    return s;
+}
+
+template <typename TIn>
+__global__ void k_quantize(TV in, TV q /* s8, ldc multiple of 4 */, float mult) {
+    const int groups = q.ldc >> 2;
+    const long total = (long)in.N * in.H * in.W * groups;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % groups);
+        const long pxl = i / groups;
+        const int x = (int)(pxl % in.W);
+        const int y = (int)((pxl / in.W) % in.H);
+        const int n = (int)(pxl / ((long)in.W * in.H));
+        const TIn *src = tv_px<TIn>(in, n, y, x);
+        uint32_t packed = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = g * 4 + j;
+            const int s = (c < in.C) ? quant_i8(to_f32(src[c]), mult) : 0;
+            packed |= (uint32_t)(s & 0xff) << (8 * j);
+        }
+        reinterpret_cast<uint32_t *>(tv_px<int8_t>(q, n, y, x))[g] = packed;
+    }
+}
+
+// INT8 convolution on CUDA cores (dp4a): acc32 = sum xq*wq (exact), then the reference's requantisation
+// epilogue: q16 = clamp(+-32767, acc32 / 32) [C truncating division]; y = (float)q16 * alpha1; y += bias;
+// leaky: y > 0 ? y : y / 10  (yolov2_forward_network_quantized.c:474-490, :598-627).
+// Weights: [ldn filters][taps][ldc_in/4 words] s8, K ordered (ky, kx, c) with zero channel padding.
+struct Int8P {
+    TV q;                     // s8 input, ldc % 4 == 0
+    TV out;                   // f32
+    const uint32_t *w;
+    const float *bias;
+    float alpha1;
+    int n, size, stride, pad, act;
+    int CW;                   // words per pixel = q.ldc/4
+    long M;
+    int32_t *acc_out;         // optional raw accumulators, NCHW (tests)
+};
+
+__device__ __forceinline__ float int8_epilogue(int acc, float alpha1, float bias, int act) {
+    int q = acc / 32;
+    if (q > 32767) q = 32767;
+    if (q < -32767) q = -32767;
+    float y = __fmul_rn((float)q, alpha1);
+    y = __fadd_rn(y, bias);
+    if (act == ACT_LEAKY) y = (y > 0.f) ? y : __fdiv_rn(y, 10.f);
+    return y;
+}
+
+static __global__ void __launch_bounds__(256) k_conv_int8_simt(Int8P p) {
+    constexpr int BM = 64, BN = 64, BKW = 8;
+    __shared__ uint32_t As[BKW][BM + 1];
+    __shared__ uint32_t Bs[BKW][BN + 1];
+    const int tid = threadIdx.x;
+    const long m0 = (long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const int OH = p.out.H, OW = p.out.W, CW = p.CW;
+    const int KW = p.size * p.size * CW;
+    const int lr = tid >> 2, lw = (tid & 3) * 2;
+    const long lm = m0 + lr;
+    const bool lvalid = lm < p.M;
+    int ln = 0, liy0 = 0, lix0 = 0;
+    if (lvalid) {
+        const int ox = (int)(lm % OW);
+        const int oy = (int)((lm / OW) % OH);
+        ln = (int)(lm / ((long)OW * OH));
+        liy0 = oy * p.stride - p.pad;
+        lix0 = ox * p.stride - p.pad;
+    }
+    const int tx = tid & 15, ty = tid >> 4;
+    int acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0;
+
+    for (int k0 = 0; k0 < KW; k0 += BKW) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int k = k0 + lw + q;
+            uint32_t a = 0, b = 0;
+            if (k < KW) {
+                const int tap = k / CW, wd = k - tap * CW;
+                if (lvalid) {
+                    const int ky = tap / p.size, kx = tap - ky * p.size;
+                    const int iy = liy0 + ky, ix = lix0 + kx;
+                    if (iy >= 0 && iy < p.q.H && ix >= 0 && ix < p.q.W)
+                        a = reinterpret_cast<const uint32_t *>(tv_px<int8_t>(p.q, ln, iy, ix))[wd];
+                }
+                b = p.w[(size_t)(n0 + lr) * KW + k];
+            }
+            As[lw + q][lr] = a;
+            Bs[lw + q][lr] = b;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BKW; ++kk) {
+            uint32_t a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = __dp4a((int)a[i], (int)b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long m = m0 + ty * 4 + i;
+        if (m >= p.M) continue;
+        const int ox = (int)(m % OW);
+        const int oy = (int)((m / OW) % OH);
+        const int n = (int)(m / ((long)OW * OH));
+        float *o = tv_px<float>(p.out, n, oy, ox);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int f = n0 + tx * 4 + j;
+            if (f >= p.n) continue;
+            if (p.acc_out) p.acc_out[(((size_t)n * p.n + f) * OH + oy) * OW + ox] = acc[i][j];
+            o[f] = int8_epilogue(acc[i][j], p.alpha1, p.bias[f], p.act);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// small layers (one thread per output element, channels innermost -> coalesced)
+// ------------------------------------------------------------------------------------------------------
+
+// forward_maxpool_layer_avx scalar build (reference additionally.c:1448-1482): window origin
+// (o*stride - pad/2), out-of-image taps ignored, init -FLT_MAX.
+template <typename T>
+__global__ void k_maxpool(TV in, TV out, int size, int stride, int pad) {
+    const long total = (long)out.N * out.H * out.W * out.C;
+    const int off = -pad / 2;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % out.C);
+        const long pxl = i / out.C;
+        const int x = (int)(pxl % out.W);
+        const int y = (int)((pxl / out.W) % out.H);
+        const int n = (int)(pxl / ((long)out.W * out.H));
+        float m = -3.402823466e+38f;
+        for (int a = 0; a < size; ++a) {
+            const int iy = off + y * stride + a;
+            if (iy < 0 || iy >= in.H) continue;
+            for (int b = 0; b < size; ++b) {
+                const int ix = off + x * stride + b;
+                if (ix < 0 || ix >= in.W) continue;
+                const float v = to_f32(tv_px<T>(in, n, iy, ix)[c]);
+                m = (v > m) ? v : m;
+            }
+        }
+        tv_px<T>(out, n, y, x)[c] = from_f32<T>(m);
+    }
+}
+
+// upsample_cpu forward (reference yolov2_forward_network.c:380-394): out = scale * in[y/stride][x/stride]
+template <typename T>
+__global__ void k_upsample(TV in, TV out, int stride, float scale) {
+    const long total = (long)out.N * out.H * out.W * out.C;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % out.C);
+        const long pxl = i / out.C;
+        const int x = (int)(pxl % out.W);
+        const int y = (int)((pxl / out.W) % out.H);
+        const int n = (int)(pxl / ((long)out.W * out.H));
+        const float v = to_f32(tv_px<T>(in, n, y / stride, x / stride)[c]);
+        tv_px<T>(out, n, y, x)[c] = from_f32<T>(__fmul_rn(scale, v));
+    }
+}
+
+// forward_shortcut_layer_cpu (reference yolov2_forward_network.c:443-449, shortcut_cpu :410-432):
+// out = act(in + from) with the general stride/sample subsampling of shortcut_cpu.
+template <typename T>
+__global__ void k_shortcut(TV in, TV from, TV out, int stride, int sample, int minw, int minh, int minc, int act) {
+    const long total = (long)out.N * out.H * out.W * out.C;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % out.C);
+        const long pxl = i / out.C;
+        const int x = (int)(pxl % out.W);
+        const int y = (int)((pxl / out.W) % out.H);
+        const int n = (int)(pxl / ((long)out.W * out.H));
+        float v = to_f32(tv_px<T>(in, n, y, x)[c]);
+        if (c < minc && (y % sample) == 0 && (x % sample) == 0) {
+            const int j = y / sample, ii = x / sample;
+            if (j < minh && ii < minw) v = __fadd_rn(v, to_f32(tv_px<T>(from, n, j * stride, ii * stride)[c]));
+        }
+        tv_px<T>(out, n, y, x)[c] = from_f32<T>(act_exact(v, act));
+    }
+}
+
+// route: copy one source into its channel slice of the concat buffer (reference yolov2_forward_network.c:318)
+template <typename T>
+__global__ void k_copy_channels(TV in, TV out /* view of the slice: C == in.C */) {
+    const long total = (long)in.N * in.H * in.W * in.C;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % in.C);
+        const long pxl = i / in.C;
+        const int x = (int)(pxl % in.W);
+        const int y = (int)((pxl / in.W) % in.H);
+        const int n = (int)(pxl / ((long)in.W * in.H));
+        tv_px<T>(out, n, y, x)[c] = tv_px<T>(in, n, y, x)[c];
+    }
+}
+
+// forward_reorg_layer_cpu (reference yolov2_forward_network.c:337-373), darknet's space-to-depth flavour:
+// out[k][j][i] = x_flat[ w2 + (out_w*stride) * (h2 + (out_h*stride) * c2) ] with the input tensor reinterpreted
+// as [in_c][out_h*stride][out_w*stride] where in_c = out_c/stride^2.
+template <typename T>
+__global__ void k_reorg(TV in, TV out, int stride) {
+    const long total = (long)out.N * out.H * out.W * out.C;
+    const int in_c = out.C / (stride * stride);
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % out.C);
+        const long pxl = i / out.C;
+        const int x = (int)(pxl % out.W);
+        const int y = (int)((pxl / out.W) % out.H);
+        const int n = (int)(pxl / ((long)out.W * out.H));
+        const int c2 = k % in_c, offset = k / in_c;
+        const int w2 = x * stride + offset % stride, h2 = y * stride + offset / stride;
+        // flat index inside one image of the source viewed as [in_c][out.H*stride][out.W*stride]
+        const long flat = w2 + (long)out.W * stride * (h2 + (long)out.H * stride * c2);
+        // map the flat NCHW index back onto the real source dims [in.C][in.H][in.W]
+        const int sx = (int)(flat % in.W);
+        const int sy = (int)((flat / in.W) % in.H);
+        const int sc = (int)(flat / ((long)in.W * in.H));
+        tv_px<T>(out, n, y, x)[k] = tv_px<T>(in, n, sy, sx)[sc];
+    }
+}
+
+// forward_yolo_layer_cpu (reference yolov2_forward_network.c:453-472): copy + logistic on entries 0,1 and
+// 4..4+classes of each anchor block.  Reads the head conv's NHWC activation, writes the NCHW f32 tensor the
+// reference decoder expects (additionally.c:4200 entry_index).
+template <typename TIn>
+__global__ void k_yolo(TV in, float *__restrict__ out, int classes) {
+    const long total = (long)in.N * in.C * in.H * in.W;
+    const int per = 4 + classes + 1;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % in.W);
+        const int y = (int)((i / in.W) % in.H);
+        const int c = (int)((i / ((long)in.W * in.H)) % in.C);
+        const int n = (int)(i / ((long)in.W * in.H * in.C));
+        float v = to_f32(tv_px<TIn>(in, n, y, x)[c]);
+        const int e = c % per;
+        if (e != 2 && e != 3) v = (float)(1.0 / (1.0 + exp(-(double)v)));
+        out[i] = v;
+    }
+}
+
+// forward_region_layer_cpu (reference yolov2_forward_network.c:511-575): per image HWC flatten (== our NHWC
+// order), float logistic on entry 4, softmax over classes (softmax_cpu :476) when softmax=1.
+// One thread per (image, cell, anchor).
+template <typename TIn>
+__global__ void k_region(TV in, float *__restrict__ out, int nanchors, int classes, int coords, int softmax) {
+    const int size = coords + classes + 1;
+    const long total = (long)in.N * in.H * in.W * nanchors;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int a = (int)(i % nanchors);
+        const long pxl = i / nanchors;
+        const int x = (int)(pxl % in.W);
+        const int y = (int)((pxl / in.W) % in.H);
+        const int n = (int)(pxl / ((long)in.W * in.H));
+        const TIn *src = tv_px<TIn>(in, n, y, x) + a * size;
+        float *o = out + (((size_t)n * in.H + y) * in.W + x) * (size_t)(nanchors * size) + (size_t)a * size;
+        for (int k = 0; k < coords; ++k) o[k] = to_f32(src[k]);
+        o[coords] = 1.0f / (1.0f + expf(-to_f32(src[coords])));
+        if (softmax) {
+            float largest = -3.402823466e+38f;
+            for (int k = 0; k < classes; ++k) { const float v = to_f32(src[coords + 1 + k]); if (v > largest) largest = v; }
+            float sum = 0.f;
+            for (int k = 0; k < classes; ++k) {
+                const float e = expf(to_f32(src[coords + 1 + k]) - largest);
+                sum += e;
+                o[coords + 1 + k] = e;
+            }
+            for (int k = 0; k < classes; ++k) o[coords + 1 + k] = __fdiv_rn(o[coords + 1 + k], sum);
+        } else {
+            for (int k = 0; k < classes; ++k) o[coords + 1 + k] = to_f32(src[coords + 1 + k]);
+        }
+    }
+}
+
+}  // namespace yb
