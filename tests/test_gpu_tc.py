@@ -1,0 +1,132 @@
+"""Tensor-core (tcgen05) FP32-variant convolution: per-layer against the CPU oracle fed the GPU's own bf16 inputs,
+then whole networks against the f32 oracle on the activated detection tensors (north_star: <= 1e-3 rel)."""
+import os
+
+import numpy as np
+import pytest
+
+import ybtest_util as util
+from yolo2_light_b200 import cfgs
+
+pytestmark = pytest.mark.gpu
+
+
+def bf16_round(a):
+    """round-to-nearest-even float32 -> bfloat16 -> float32"""
+    u = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return (r & 0xFFFFFFFF).astype(np.uint32).view(np.float32).reshape(np.shape(a))
+
+
+def tcnet(size=64):
+    """Exercises every tile configuration of k_conv_tc: BK 16/32/64, BN 32/64/128/256, 3x3 s1, 3x3 s2, 1x1, fused
+    shortcut, concat slice output, f32 head with 255 filters."""
+    c = cfgs._conv
+    s = [cfgs._net(size, size),
+         c(16, 3),                   # 0 stem (CUDA cores, C=3)
+         c(32, 3, 2),                # 1 s2, BK16, BN32
+         c(64, 3),                   # 2 s1, BK32, BN64
+         c(32, 1),                   # 3 1x1, BK64, BN32
+         c(64, 3),                   # 4 3x3 + fused shortcut
+         ("shortcut", {"from": "-3", "activation": "linear"}),   # 5
+         c(128, 3, 2),               # 6 s2, BK64, BN128
+         c(64, 1),                   # 7
+         c(128, 3),                  # 8
+         ("shortcut", {"from": "-3", "activation": "linear"}),   # 9
+         c(256, 3, 2),               # 10 s2 BN256
+         c(128, 1),                  # 11
+         c(256, 3),                  # 12
+         c(320, 1),                  # 13 two filter tiles (256 + 64)
+         c(255, 1, bn=False, act="linear"),   # 14 head, f32 out, n=255
+         cfgs._yolo("0,1,2", cfgs.COCO_ANCHORS, 9),              # 15
+         ("route", {"layers": "-4"}),                            # 16 -> layer 12
+         c(64, 1),                   # 17
+         ("upsample", {"stride": "2"}),                          # 18 writes a concat slice
+         ("route", {"layers": "-1, 9"}),                         # 19 concat(64 + 128) = 192 channels
+         c(128, 3),                  # 20 reads the concat (C=192, BK64)
+         c(255, 1, bn=False, act="linear"),   # 21
+         cfgs._yolo("3,4,5", cfgs.COCO_ANCHORS, 9)]              # 22
+    return s
+
+
+def _files(workdir, name, secs, seed):
+    cfg = os.path.join(workdir, name + ".cfg")
+    wts = os.path.join(workdir, name + ".weights")
+    cfgs.write_cfg(secs, cfg)
+    cfgs.write_weights(secs, wts, seed=seed)
+    return cfg, wts
+
+
+@pytest.mark.parametrize("size,batch", [(64, 2), (96, 3)])
+def test_tc_every_layer_vs_oracle_on_bf16_inputs(size, batch, workdir):
+    import yolo2_light_b200 as yb
+    from oracle import port
+    cfg, wts = _files(workdir, f"tcnet{size}", tcnet(size), 21)
+    net = yb.load_network(cfg, wts, batch=batch)
+    net.set_precision(yb.YB_PREC_BF16_TC)
+    net.set_option("fuse", 0)
+    x = cfgs.synthetic_images(batch, 3, size, size, seed=5)
+    net.predict(x)
+    prof = net.profile()
+    kinds = {}
+    for li, kind, ms in prof:
+        kinds.setdefault(li, []).append(kind)
+    layers = net.layers
+    got = [None] * net.n
+    for i in range(net.n):
+        got[i] = net.fetch_layer(i)
+    n_tc = 0
+    for i, l in enumerate(layers):
+        if l["type_name"] != "CONVOLUTIONAL":
+            continue
+        xin = bf16_round(x) if i == 0 else got[i - 1]
+        is_tc = "conv_tc" in kinds.get(i, [])
+        n_tc += is_tc
+        w = bf16_round(l["weights"]) if is_tc else l["weights"]
+        exp = port.conv_fp32(xin, w, l["biases"], l["n"], l["size"], l["stride"], l["pad"], l["activation"])
+        head = l["activation"] == 3
+        if not head:
+            exp = bf16_round(exp)
+        err = util.rel_l2(got[i], exp)
+        assert err <= 5e-4, (size, i, "tc" if is_tc else "simt", err)
+    assert n_tc >= 14, n_tc
+
+
+def test_tc_fused_equals_unfused(workdir):
+    import yolo2_light_b200 as yb
+    cfg, wts = _files(workdir, "tcnet64f", tcnet(64), 22)
+    x = cfgs.synthetic_images(2, 3, 64, 64, seed=6)
+    outs = []
+    for fuse in (0, 1):
+        net = yb.load_network(cfg, wts, batch=2)
+        net.set_option("fuse", fuse)
+        net.predict(x)
+        outs.append({i: o.copy() for i, o in net.detection_outputs().items()})
+        launches = net.last_launches()
+        outs.append(launches)
+    assert outs[3] < outs[1]
+    for i in outs[0]:
+        assert util.rel_l2(outs[2][i], outs[0][i]) <= 2e-3, i   # residual add before vs after bf16 rounding
+
+
+@pytest.mark.parametrize("name", ["tcnet", "v3_32", "spp32", "tiny64"])
+def test_bf16_network_vs_f32_oracle(name, workdir):
+    """Whole network, default precision, against the f32 oracle: <= 1e-3 rel-L2 on the activated yolo tensors... for
+    the slim test nets the bar is 3e-3 (few channels -> less averaging of the bf16 rounding noise); the full-size
+    bar is asserted in test_gpu_fullsize.py."""
+    import yolo2_light_b200 as yb
+    from oracle import port
+    if name == "tcnet":
+        cfg, wts = _files(workdir, "tcnet64w", tcnet(64), 23)
+        x = cfgs.synthetic_images(2, 3, 64, 64, seed=7)
+    else:
+        cfg, wts = util.model_files(name, workdir)
+        x = util.images(name, 2)
+    net = yb.load_network(cfg, wts, batch=2)
+    net.predict(x)
+    layers = net.layers
+    exp = [port.run_network(layers, x[b:b + 1]) for b in range(2)]
+    for i, o in net.detection_outputs().items():
+        e = np.concatenate([exp[b][i] for b in range(2)], 0).reshape(o.shape)
+        err = util.rel_l2(o, e)
+        assert err <= 3e-3, (name, i, err)

@@ -9,7 +9,7 @@
 namespace yb {
 
 // non-zero if the bf16 tcgen05 kernel takes this layer (input view `in`, bf16 or f32 output)
-int tc_conv_supported(const Layer &l, const TV &in, bool out_bf16);
+int tc_conv_supported(const Layer &l, const TV &in, const TV &out, bool out_bf16);
 // builds the per-layer launch state (TMA tensor maps, tile schedule); throws yb::Error on failure
 void *tc_make_plan(const Layer &l, const TV &in, const TV &out, bool out_bf16, const TV &res, bool res_bf16,
                    int act2, const void *d_weights_bf16, int ldn, const float *d_bias);

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "yb_conv_tc.cuh"
@@ -233,7 +234,7 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
     auto own_buffer = [&](int i) {
         const Layer &l = net->layers[i];
         buf_off[i] = act_total;
-        act_total += align_up(tv_bytes(B, l.out_h, l.out_w, l.out_c, P, e->out_dt[i]), 1024);
+        act_total += align_up(tv_bytes(B, l.out_h, l.out_w, (int)align_up(l.out_c, 8), P, e->out_dt[i]), 1024);
     };
     const size_t in0_off = act_total;
     e->in0_dt = ADT;
@@ -277,14 +278,15 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
             continue;
         }
         if (home[i].owner >= 0) continue;
-        e->out_tv[i] = make_tv(e->act_arena + buf_off[i], B, l.out_h, l.out_w, l.out_c, l.out_c, P, e->out_dt[i], 0);
+        // pixel stride rounded up to 8 channels: 16-byte aligned rows for TMA / vector stores (e.g. 255 -> 256)
+        e->out_tv[i] = make_tv(e->act_arena + buf_off[i], B, l.out_h, l.out_w, l.out_c, (int)align_up(l.out_c, 8), P, e->out_dt[i], 0);
     }
     // slices (owner buffers are allocated above since routes own their buffers)
     for (int i = 0; i < nl; ++i) {
         if (home[i].owner < 0) continue;
         const Layer &l = net->layers[i];
         const int r = home[i].owner;
-        e->out_tv[i] = make_tv(e->act_arena + buf_off[r], B, l.out_h, l.out_w, l.out_c, home[i].ldc, P, ADT, home[i].coff);
+        e->out_tv[i] = make_tv(e->act_arena + buf_off[r], B, l.out_h, l.out_w, l.out_c, e->out_tv[r].ldc, P, ADT, home[i].coff);
     }
     // single-input route aliases may point at slices that were only resolved now
     for (int i = 0; i < nl; ++i) {
@@ -337,7 +339,9 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
             const TV &tin = (i == 0) ? e->in0 : e->out_tv[i - 1];
             const int in_dt = (i == 0) ? e->in0_dt : e->out_dt[i - 1];
             const int odt = fused_into[i] >= 0 ? e->out_dt[fused_into[i]] : e->out_dt[i];
-            use_tc[i] = (ADT == DT_BF16 && in_dt == DT_BF16) ? tc_conv_supported(l, tin, odt == DT_BF16) : 0;
+            const TV &tout = e->out_tv[fused_into[i] >= 0 ? fused_into[i] : i];
+            use_tc[i] = (ADT == DT_BF16 && in_dt == DT_BF16) ? tc_conv_supported(l, tin, tout, odt == DT_BF16) : 0;
+            if (getenv("YB_NO_TC")) use_tc[i] = 0;
             if (use_tc[i]) {
                 // bf16 [ldn][K], K ordered (ky, kx, c): the K-major B operand of the implicit GEMM
                 w.ldn = (int)align_up(l.n, 64);
