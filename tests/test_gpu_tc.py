@@ -79,7 +79,7 @@ def test_tc_every_layer_vs_oracle_on_bf16_inputs(size, batch, workdir):
     for i, l in enumerate(layers):
         if l["type_name"] != "CONVOLUTIONAL":
             continue
-        xin = bf16_round(x) if i == 0 else got[i - 1]
+        xin = x if i == 0 else got[i - 1]   # the stem kernel reads the caller's f32 NCHW image directly
         is_tc = "conv_tc" in kinds.get(i, [])
         n_tc += is_tc
         w = bf16_round(l["weights"]) if is_tc else l["weights"]

@@ -167,6 +167,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // bias (folded batch-norm) for all filter tiles -> shared memory, once per CTA
+    float *bias_s = reinterpret_cast<float *>(smem_raw + (tmem_slot + 16u - smem_u32(smem_raw)));
+    for (int i = threadIdx.x; i < p.nt * p.BN; i += TC_THREADS) bias_s[i] = (i < p.n) ? __ldg(p.bias + i) : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -229,9 +232,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
     } else {
         // ======================= epilogue (warps 2..5) =======================
+        // Per 64-column slab: issue both TMEM loads and the residual loads first, wait once, then do the math and
+        // the stores -- global-load latency is paid once per slab instead of once per value (the first version
+        // was epilogue-bound on exactly that, profiles/r01_notes.md).
         const int q = warp & 3;                   // TMEM lane quarter this warp may access
         const int r = q * 32 + lane;              // accumulator row == pixel within the tile
         const int tx = r & (p.TW - 1), ty = r >> p.TWlog2;
+        const bool leaky = p.act == ACT_LEAKY, leaky2 = p.act2 == ACT_LEAKY;
         int acc = 0; uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
             const int n_idx = t % p.nt;
@@ -244,69 +251,88 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const bool valid = (img < p.N) && (oy >= 0) && (oy < p.OH) && (ox < p.OW);
             const long pix = ((long)(img * p.OHp + oy + 1) * p.OWp + ox + 1);
             char *orow = p.out + pix * p.out_ldc * (p.out_bf16 ? 2 : 4);
-            const char *rrow = p.res ? p.res + pix * p.res_ldc * (p.res_bf16 ? 2 : 4) : nullptr;
+            const char *rrow = (p.res && valid) ? p.res + pix * p.res_ldc * 2 : nullptr;
+            const float *bs = bias_s + n0;
+
+            // residual for the first slab can be fetched before the accumulator is ready
+            uint4 rv[2][4];
+            auto load_res = [&](int f0, uint4 (&dst)[4]) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    dst[g] = make_uint4(0u, 0u, 0u, 0u);
+                    if (rrow && (n0 + f0 + g * 8) < p.n_store)
+                        dst[g] = __ldg(reinterpret_cast<const uint4 *>(rrow + (size_t)(n0 + f0) * 2) + g);
+                }
+            };
+            load_res(0, rv[0]);
+            if (p.BN > 32) load_res(32, rv[1]);
 
             mbar_wait(tfull_bar(acc), acc_phase, 3);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
-            for (int f0 = 0; f0 < p.BN; f0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(taddr + (uint32_t)f0, v);
+
+            auto finish = [&](const uint32_t (&v)[32], const uint4 (&rr)[4], int f0) {
+                if (!valid || (n0 + f0) >= p.n_store) return;
+                float x[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float a = __uint_as_float(v[j]) + bs[f0 + j];
+                    x[j] = leaky ? ((a > 0.f) ? a : 0.1f * a) : a;
+                }
+                if (p.res) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const uint32_t w[4] = {rr[g].x, rr[g].y, rr[g].z, rr[g].w};
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            x[g * 8 + 2 * h] += __uint_as_float(w[h] << 16);
+                            x[g * 8 + 2 * h + 1] += __uint_as_float(w[h] & 0xffff0000u);
+                        }
+                    }
+                    if (leaky2) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) x[j] = (x[j] > 0.f) ? x[j] : 0.1f * x[j];
+                    }
+                }
+                if (p.out_bf16) {
+                    uint4 *op = reinterpret_cast<uint4 *>(orow + (size_t)(n0 + f0) * 2);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (n0 + f0 + g * 8 >= p.n_store) break;
+                        uint4 o;
+                        o.x = pack_bf16x2(x[g * 8 + 0], x[g * 8 + 1]);
+                        o.y = pack_bf16x2(x[g * 8 + 2], x[g * 8 + 3]);
+                        o.z = pack_bf16x2(x[g * 8 + 4], x[g * 8 + 5]);
+                        o.w = pack_bf16x2(x[g * 8 + 6], x[g * 8 + 7]);
+                        op[g] = o;
+                    }
+                } else {
+                    float4 *op = reinterpret_cast<float4 *>(orow + (size_t)(n0 + f0) * 4);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        if (n0 + f0 + g * 4 >= p.n_store) break;
+                        op[g] = make_float4(x[g * 4 + 0], x[g * 4 + 1], x[g * 4 + 2], x[g * 4 + 3]);
+                    }
+                }
+            };
+
+            if (p.BN == 32) {
+                uint32_t v0[32];
+                tmem_ld32(taddr, v0);
                 tmem_ld_wait();
-                if (valid && (n0 + f0) < p.n_store) {
-                    float x[32];
+                finish(v0, rv[0], 0);
+            } else {
+                for (int f0 = 0; f0 < p.BN; f0 += 64) {
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(taddr + (uint32_t)f0, v0);
+                    tmem_ld32(taddr + (uint32_t)f0 + 32u, v1);
+                    tmem_ld_wait();
+                    uint4 r0[4], r1[4];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int f = n0 + f0 + j;
-                        float a = __uint_as_float(v[j]) + ((f < p.n) ? __ldg(p.bias + f) : 0.f);
-                        if (p.act == ACT_LEAKY) a = (a > 0.f) ? a : 0.1f * a;
-                        x[j] = a;
-                    }
-                    if (rrow) {
-                        if (p.res_bf16) {
-                            const uint4 *rp = reinterpret_cast<const uint4 *>(rrow + (size_t)(n0 + f0) * 2);
-#pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                if (n0 + f0 + g * 8 >= p.n_store) break;
-                                const uint4 rv = __ldg(rp + g);
-                                const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                                for (int h = 0; h < 4; ++h) {
-                                    x[g * 8 + 2 * h] += __uint_as_float(w[h] << 16);
-                                    x[g * 8 + 2 * h + 1] += __uint_as_float(w[h] & 0xffff0000u);
-                                }
-                            }
-                        } else {
-                            const float *rp = reinterpret_cast<const float *>(rrow) + (n0 + f0);
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (n0 + f0 + j < p.n) x[j] += __ldg(rp + j);
-                        }
-                        if (p.act2 == ACT_LEAKY) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) x[j] = (x[j] > 0.f) ? x[j] : 0.1f * x[j];
-                        }
-                    }
-                    if (p.out_bf16) {
-                        uint4 *op = reinterpret_cast<uint4 *>(orow + (size_t)(n0 + f0) * 2);
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            if (n0 + f0 + g * 8 >= p.n_store) break;
-                            uint4 o;
-                            o.x = pack_bf16x2(x[g * 8 + 0], x[g * 8 + 1]);
-                            o.y = pack_bf16x2(x[g * 8 + 2], x[g * 8 + 3]);
-                            o.z = pack_bf16x2(x[g * 8 + 4], x[g * 8 + 5]);
-                            o.w = pack_bf16x2(x[g * 8 + 6], x[g * 8 + 7]);
-                            op[g] = o;
-                        }
-                    } else {
-                        float4 *op = reinterpret_cast<float4 *>(orow + (size_t)(n0 + f0) * 4);
-#pragma unroll
-                        for (int g = 0; g < 8; ++g) {
-                            if (n0 + f0 + g * 4 >= p.n_store) break;
-                            op[g] = make_float4(x[g * 4 + 0], x[g * 4 + 1], x[g * 4 + 2], x[g * 4 + 3]);
-                        }
-                    }
+                    for (int g = 0; g < 4; ++g) { r0[g] = rv[0][g]; r1[g] = rv[1][g]; }
+                    if (f0 + 64 < p.BN) { load_res(f0 + 64, rv[0]); load_res(f0 + 96, rv[1]); }   // next slab in flight
+                    finish(v0, r0, f0);
+                    finish(v1, r1, f0 + 32);
                 }
             }
             tc_fence_before();
@@ -399,7 +425,8 @@ void *tc_make_plan(const Layer &l, const TV &in, const TV &out, bool out_bf16, c
     p.num_tiles = p.xt * p.jt * p.nt;
     p.a_bytes = (uint32_t)(TC_BM * BK * 2);
     p.stage_bytes = p.a_bytes + (uint32_t)(BN * BK * 2);
-    p.stages = (int)std::min<size_t>(8, (200 * 1024) / p.stage_bytes);
+    p.nt = (l.n + BN - 1) / BN;
+    p.stages = (int)std::min<size_t>(8, (200 * 1024 - sizeof(float) * (size_t)p.nt * BN) / p.stage_bytes);
     if (p.stages < 2) fatal_throw("tc plan: tile does not fit shared memory");
     // UMMA instruction descriptor (kind::f16): D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
@@ -413,6 +440,7 @@ void *tc_make_plan(const Layer &l, const TV &in, const TV &out, bool out_bf16, c
     if (!out_bf16 && (out.ldc % 4 != 0)) fatal_throw("tc plan: f32 output rows must be 16-byte aligned");
     p.res = res.base; p.res_ldc = res.ldc; p.res_bf16 = res_bf16 ? 1 : 0;
     if (res.base && (res.H != l.out_h || res.W != l.out_w || res.C != l.n)) fatal_throw("tc plan: residual shape mismatch");
+    if (res.base && !res_bf16) fatal_throw("tc plan: residual must be bf16");
     if (res.base && res_bf16 && (res.ldc % 8 != 0 || (reinterpret_cast<uintptr_t>(res.base) & 15))) fatal_throw("tc plan: residual alignment");
     p.bias = d_bias; p.act = l.activation; p.act2 = act2;
     uint32_t cols = 32; while (cols < (uint32_t)(TC_ACC * BN)) cols *= 2;
@@ -455,7 +483,8 @@ void *tc_make_plan(const Layer &l, const TV &in, const TV &out, bool out_bf16, c
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     plan->grid = std::min(p.num_tiles, sms);
-    plan->smem = (size_t)p.stages * p.stage_bytes + 1024 /*alignment slack*/ + 8 * (2 * p.stages + 2 * TC_ACC) + 16;
+    plan->smem = (size_t)p.stages * p.stage_bytes + 1024 /*alignment slack*/ + 8 * (2 * p.stages + 2 * TC_ACC) + 16 +
+                 sizeof(float) * (size_t)p.nt * BN /*bias*/;
     if (cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
         fatal_throw("cudaFuncSetAttribute(k_conv_tc) failed");
     return plan;

@@ -72,6 +72,8 @@ struct Engine {
     cudaGraphExec_t graph_exec = nullptr;
     bool graph_failed = false;
     std::vector<void *> tc_plans;      // opaque per-layer state of the tensor-core path (tensor maps)
+    std::function<void(const float *, cudaStream_t)> first_op;   // consumes the caller's NCHW images (pointer varies per call)
+    int first_kind = OP_INPUT, first_layer = -1;
     ~Engine();
 };
 
@@ -399,11 +401,40 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
 
     // ---- op list -----------------------------------------------------------------------------------
     Engine *E = e.get();
+    bool stem_fused = false;
     {
-        TV in0 = e->in0;
-        const int dt = e->in0_dt;
-        e->ops.push_back(Op{OP_INPUT, -1, nullptr});   // launched specially (input pointer varies per call)
-        (void)in0; (void)dt;
+        // ops[0] consumes the caller's NCHW f32 images.  Usually that is the stem convolution itself (3 input
+        // channels, 3x3/1/1), reading NCHW directly; otherwise a plain NCHW -> padded-NHWC conversion.
+        const Layer &l0 = net->layers[0];
+        const bool stem_ok = l0.type == YB_CONVOLUTIONAL && conv_variant(0) == 0 && !use_tc[0] && l0.c == 3 &&
+                             l0.size == 3 && l0.stride == 1 && l0.pad == 1 && (l0.n == 16 || l0.n == 32) &&
+                             fused_into[0] < 0 && e->out_tv[0].base && !getenv("YB_NO_STEM") &&
+                             (e->out_dt[0] == DT_F32 || (e->out_tv[0].ldc % 8 == 0));
+        if (stem_ok) {
+            stem_fused = true;
+            const TV tout = e->out_tv[0];
+            const float *w = reinterpret_cast<const float *>(e->w_arena + cw[0].w_f32);
+            const float *bias = reinterpret_cast<const float *>(e->w_arena + cw[0].bias);
+            const int ldw = cw[0].ldw, act = l0.activation, H = l0.h, W = l0.w, nf = l0.n, odt = e->out_dt[0];
+            const long total = (long)B * H * W;
+            const int grid = (int)((total + 127) / 128);
+            e->first_kind = OP_CONV_SIMT; e->first_layer = 0;
+            e->first_op = [=](const float *din, cudaStream_t s) {
+                if (nf == 32 && odt == DT_BF16) k_conv_stem<32, __nv_bfloat16><<<grid, 128, 0, s>>>(din, tout, w, ldw, bias, act, H, W);
+                else if (nf == 32) k_conv_stem<32, float><<<grid, 128, 0, s>>>(din, tout, w, ldw, bias, act, H, W);
+                else if (odt == DT_BF16) k_conv_stem<16, __nv_bfloat16><<<grid, 128, 0, s>>>(din, tout, w, ldw, bias, act, H, W);
+                else k_conv_stem<16, float><<<grid, 128, 0, s>>>(din, tout, w, ldw, bias, act, H, W);
+            };
+        } else {
+            const TV in0 = e->in0;
+            const int dt = e->in0_dt;
+            const int g = grid_for((long)in0.N * in0.H * in0.W);
+            e->first_op = [=](const float *din, cudaStream_t s) {
+                if (dt == DT_F32) k_input_nchw_to_nhwc<float><<<g, 256, 0, s>>>(din, in0);
+                else k_input_nchw_to_nhwc<__nv_bfloat16><<<g, 256, 0, s>>>(din, in0);
+            };
+        }
+        e->ops.push_back(Op{e->first_kind, e->first_layer, nullptr});   // launched specially: pointer varies per call
     }
     for (int i = 0; i < nl; ++i) {
         const Layer &l = net->layers[i];
@@ -413,6 +444,7 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
         auto need_prev = [&]() {
             if (!prev_ok) fatal_throw("engine: layer " + std::to_string(i) + " has no image input");
         };
+        if (i == 0 && stem_fused) continue;
         switch (l.type) {
         case YB_CONVOLUTIONAL: {
             need_prev();
@@ -648,12 +680,7 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
     return e;
 }
 
-static void launch_input(Engine *e, const float *d_in, cudaStream_t s) {
-    const TV in0 = e->in0;
-    const int g = grid_for((long)in0.N * in0.H * in0.W);
-    if (e->in0_dt == DT_F32) k_input_nchw_to_nhwc<float><<<g, 256, 0, s>>>(d_in, in0);
-    else k_input_nchw_to_nhwc<__nv_bfloat16><<<g, 256, 0, s>>>(d_in, in0);
-}
+static void launch_input(Engine *e, const float *d_in, cudaStream_t s) { e->first_op(d_in, s); }
 
 void engine_upload_input(Engine *e, const float *host_input, void *stream) {
     cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
@@ -668,6 +695,7 @@ void engine_forward(Engine *e, const void *d_input, void *stream) {
     CUDA_OK(cudaSetDevice(e->opt.device));   // thread identity may change per call (threading)
     const float *din = d_input ? reinterpret_cast<const float *>(d_input) : e->d_input;
     launch_input(e, din, s);
+    if (!e->graph_exec && !e->graph_failed && getenv("YB_NO_GRAPH")) e->graph_failed = true;   // profiling aid
     if (!e->graph_exec && !e->graph_failed) {
         // capture everything after the input conversion once
         cudaGraph_t graph = nullptr;

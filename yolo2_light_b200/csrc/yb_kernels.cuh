@@ -182,6 +182,77 @@ __global__ void __launch_bounds__(256) k_conv_simt(ConvP p) {
 }
 
 // ------------------------------------------------------------------------------------------------------
+// stem convolution (network input, 3 channels): 3x3 / stride 1 / pad 1 straight from the caller's NCHW f32 image
+// (reference input contract additionally.c:3093-3103) to padded-NHWC output -- fuses the layout conversion, so
+// the image is read exactly once and no NHWC copy of it is ever written.  One thread per output pixel, all NF
+// filters in registers, weights [27][NF] broadcast from shared memory.  Accumulation order (ky, kx, c) matches
+// k_conv_simt.
+// ------------------------------------------------------------------------------------------------------
+template <int NF, typename TOut>
+__global__ void __launch_bounds__(128) k_conv_stem(const float *__restrict__ in, TV out, const float *__restrict__ w /*[27][ldw]*/,
+                                                   int ldw, const float *__restrict__ bias, int act, int H, int W) {
+    __shared__ float ws[27 * NF];
+    __shared__ float bs[NF];
+    for (int i = threadIdx.x; i < 27 * NF; i += blockDim.x) ws[i] = w[(i / NF) * ldw + (i % NF)];
+    for (int i = threadIdx.x; i < NF; i += blockDim.x) bs[i] = bias[i];
+    __syncthreads();
+    const long total = (long)out.N * H * W;
+    const long p = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    const int x = (int)(p % W);
+    const int y = (int)((p / W) % H);
+    const int n = (int)(p / ((long)W * H));
+    const float *img = in + (size_t)n * 3 * H * W;
+    float acc[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) acc[f] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = y + ky - 1;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int ix = x + kx - 1;
+            const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float v = ok ? __ldg(img + ((size_t)c * H + iy) * W + ix) : 0.f;
+                const float4 *wp = reinterpret_cast<const float4 *>(ws + ((ky * 3 + kx) * 3 + c) * NF);
+#pragma unroll
+                for (int f4 = 0; f4 < NF / 4; ++f4) {
+                    const float4 wv = wp[f4];
+                    acc[f4 * 4 + 0] = fmaf(v, wv.x, acc[f4 * 4 + 0]);
+                    acc[f4 * 4 + 1] = fmaf(v, wv.y, acc[f4 * 4 + 1]);
+                    acc[f4 * 4 + 2] = fmaf(v, wv.z, acc[f4 * 4 + 2]);
+                    acc[f4 * 4 + 3] = fmaf(v, wv.w, acc[f4 * 4 + 3]);
+                }
+            }
+        }
+    }
+    TOut *o = tv_px<TOut>(out, n, y, x);
+    if constexpr (sizeof(TOut) == 2) {
+        uint4 *op = reinterpret_cast<uint4 *>(o);
+#pragma unroll
+        for (int g = 0; g < NF / 8; ++g) {
+            float t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float a = acc[g * 8 + j] + bs[g * 8 + j];
+                t[j] = (act == ACT_LEAKY) ? ((a > 0.f) ? a : 0.1f * a) : act_exact(a, act);
+            }
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(t[0], t[1]), h1 = __floats2bfloat162_rn(t[2], t[3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(t[4], t[5]), h3 = __floats2bfloat162_rn(t[6], t[7]);
+            uint4 v;
+            v.x = *reinterpret_cast<uint32_t *>(&h0); v.y = *reinterpret_cast<uint32_t *>(&h1);
+            v.z = *reinterpret_cast<uint32_t *>(&h2); v.w = *reinterpret_cast<uint32_t *>(&h3);
+            op[g] = v;
+        }
+    } else {
+#pragma unroll
+        for (int f = 0; f < NF; ++f) o[f] = from_f32<TOut>(act_exact(acc[f] + bs[f], act));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // BIT1-XNOR path (reference yolov2_forward_network.c:116-203).
 // k_binarize: f32 activation -> 1 bit per channel, bit = (x > 0), 32 channels per word, padded NHWC with a
 // zero (== -1, F9) border.  One warp per (pixel, word): coalesced read + __ballot_sync.
