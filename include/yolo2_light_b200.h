@@ -137,6 +137,15 @@ float *yb_network_predict(yb_network *net, const float *input);
  * activation is not LINEAR; everything else as in yb_network_predict with f32 activations. */
 float *yb_network_predict_quantized(yb_network *net, const float *input);
 
+/* Pipelined form of the two calls above for throughput serving: yb_network_submit enqueues one batch (H2D of
+ * `input` on a copy stream, the forward on the compute stream, D2H of the yolo/region tensors on a third stream)
+ * and returns a ticket immediately; yb_network_collect blocks until that batch is done and points the layers'
+ * host outputs at its results (valid until the ticket's slot is reused, i.e. for the next 2 submits).  Up to 3
+ * batches may be in flight, so the copies of batch k+1 / k-1 overlap the compute of batch k.  `input` should be
+ * pinned (yb_alloc_pinned) and must stay untouched until its ticket has been collected. */
+int yb_network_submit(yb_network *net, const float *input, int quantized);
+int yb_network_collect(yb_network *net, int ticket, int quantized);
+
 /* Host output (NCHW for yolo, HWC-flattened for region, as the reference lays them out) of layer i after a
  * predict call; only YOLO/REGION layers (and the last layer) are kept on the host. */
 const float *yb_network_layer_output(const yb_network *net, int i, int *count);

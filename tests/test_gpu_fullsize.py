@@ -119,3 +119,33 @@ def test_spp_608_runs_and_matches_f32_cuda_core_path(workdir):
     b.predict(x)
     for i, o in a.detection_outputs().items():
         assert util.rel_l2(o, b.layer_output(i)) <= 1e-3, i
+
+
+def test_pipelined_submit_collect_equals_predict(workdir):
+    """yb_network_submit/collect (copies overlapped with compute, 3 batches in flight) returns exactly what the
+    synchronous predict returns, batch after batch, including when slots are reused."""
+    import yolo2_light_b200 as yb
+    secs = cfgs.yolov3_tiny(416, 416)
+    cfg, wts = _files(workdir, "tiny_416", secs)
+    B = 4
+    net = yb.load_network(cfg, wts, batch=B)
+    batches = [cfgs.synthetic_images(B, 3, 416, 416, seed=100 + 10 * k) for k in range(7)]
+    expect = []
+    for x in batches:
+        net.predict(x)
+        expect.append({i: o.copy() for i, o in net.detection_outputs().items()})
+    pinned = [yb.PinnedBuffer(B * 3 * 416 * 416) for _ in range(3)]
+    inflight, got = [], []
+    for k, x in enumerate(batches):
+        if len(inflight) == 3:
+            got.append({i: o.copy() for i, o in net.collect(inflight.pop(0)).items()})
+        pinned[k % 3].array[:] = x.ravel()
+        inflight.append(net.submit(pinned[k % 3].array))
+    while inflight:
+        got.append({i: o.copy() for i, o in net.collect(inflight.pop(0)).items()})
+    assert len(got) == len(expect)
+    for g, e in zip(got, expect):
+        for i in e:
+            assert util.bits_equal(g[i], e[i])
+    with pytest.raises(yb.YbError):
+        net.collect(0)   # nothing in flight

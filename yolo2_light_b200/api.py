@@ -90,6 +90,8 @@ def lib():
         "yb_network_set_option": (C.c_int, [vp, C.c_char_p, C.c_int]),
         "yb_network_predict": (fp, [vp, vp]),
         "yb_network_predict_quantized": (fp, [vp, vp]),
+        "yb_network_submit": (C.c_int, [vp, vp, C.c_int]),
+        "yb_network_collect": (C.c_int, [vp, C.c_int, C.c_int]),
         "yb_network_layer_output": (fp, [vp, C.c_int, ip]),
         "yb_network_forward_device": (C.c_int, [vp, vp, C.c_int, vp]),
         "yb_network_sync_outputs": (C.c_int, [vp, C.c_int, vp]),
@@ -120,7 +122,7 @@ EXPORTED_SYMBOLS = [
     "yb_network_from_layers", "yb_free_network", "yb_network_num_layers", "yb_network_dims", "yb_network_layer",
     "yb_network_layer_outputs", "yb_network_input_calibration", "yb_set_batch_network", "yb_network_set_device",
     "yb_network_set_precision", "yb_network_set_option", "yb_network_predict", "yb_network_predict_quantized",
-    "yb_network_layer_output", "yb_network_forward_device", "yb_network_sync_outputs", "yb_network_fetch_layer",
+    "yb_network_submit", "yb_network_collect", "yb_network_layer_output", "yb_network_forward_device", "yb_network_sync_outputs", "yb_network_fetch_layer",
     "yb_network_fetch_counts", "yb_forward_convolutional_layer", "yb_network_weight_arena",
     "yb_network_last_launches", "yb_network_profile", "yb_op_kind_name", "yb_get_network_boxes", "yb_alloc_pinned",
     "yb_free_pinned",
@@ -226,6 +228,23 @@ class Network:
         p = f(self._h, x.ctypes.data_as(C.c_void_p))
         _check(bool(p))
         return self.layer_output(self.n - 1)
+
+    def submit(self, images: np.ndarray, quantized: bool = False) -> int:
+        """Pipelined predict: enqueue one batch, returns a ticket (see yb_network_submit)."""
+        x = images if (isinstance(images, np.ndarray) and images.dtype == np.float32 and images.flags.c_contiguous) \
+            else np.ascontiguousarray(images, dtype=np.float32)
+        if x.size != self.batch * self.c * self.h * self.w:
+            raise YbError("submit: wrong input size")
+        self._inflight = getattr(self, "_inflight", {})
+        t = lib().yb_network_submit(self._h, x.ctypes.data_as(C.c_void_p), int(quantized))
+        _check(t >= 0)
+        self._inflight[t] = x   # keep the host buffer alive until collected
+        return t
+
+    def collect(self, ticket: int, quantized: bool = False) -> dict:
+        _check(lib().yb_network_collect(self._h, ticket, int(quantized)) == 0)
+        getattr(self, "_inflight", {}).pop(ticket, None)
+        return self.detection_outputs()
 
     def layer_output(self, i: int) -> np.ndarray:
         """Host output of a YOLO / REGION / last layer after predict (view on pinned memory; copy to keep)."""

@@ -230,6 +230,22 @@ float *yb_network_predict_quantized(yb_network *n, const float *input) {
     YB_TRY return predict_common(n, input, 1); YB_CATCH(nullptr)
 }
 
+int yb_network_submit(yb_network *n, const float *input, int quantized) {
+    YB_TRY
+    Engine *e = get_engine(n, quantized);
+    const int t = engine_submit(e, input);
+    n->net.last_launches = engine_num_launches(e);
+    return t;
+    YB_CATCH(-1)
+}
+int yb_network_collect(yb_network *n, int ticket, int quantized) {
+    YB_TRY
+    Engine *e = get_engine(n, quantized);
+    engine_collect(e, &n->net, ticket);
+    return 0;
+    YB_CATCH(-1)
+}
+
 const float *yb_network_layer_output(const yb_network *n, int i, int *count) {
     if (i < 0 || i >= (int)n->net.layers.size()) return nullptr;
     if (count) *count = (int)n->net.layers[i].output_count;

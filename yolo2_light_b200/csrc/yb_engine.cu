@@ -74,6 +74,16 @@ struct Engine {
     std::vector<void *> tc_plans;      // opaque per-layer state of the tensor-core path (tensor maps)
     std::function<void(const float *, cudaStream_t)> first_op;   // consumes the caller's NCHW images (pointer varies per call)
     int first_kind = OP_INPUT, first_layer = -1;
+    // ---- pipelined end-to-end path: H2D(k+1) | compute(k) | D2H(k-1) on three streams -----------------
+    struct Slot {
+        float *d_in = nullptr;
+        std::vector<float *> d_out, h_out;
+        cudaEvent_t ev_in = nullptr, ev_comp = nullptr, ev_done = nullptr;
+        bool busy = false;
+    };
+    std::vector<Slot> slots;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    int next_slot = 0;
     ~Engine();
 };
 
@@ -84,6 +94,16 @@ Engine::~Engine() {
     for (float *p : d_final) if (p) cudaFree(p);
     for (int32_t *p : d_counts) if (p) cudaFree(p);
     for (void *p : tc_plans) tc_free_plan(p);
+    for (Slot &sl : slots) {
+        if (sl.d_in) cudaFree(sl.d_in);
+        for (float *p : sl.d_out) if (p) cudaFree(p);
+        for (float *p : sl.h_out) if (p) cudaFreeHost(p);
+        if (sl.ev_in) cudaEventDestroy(sl.ev_in);
+        if (sl.ev_comp) cudaEventDestroy(sl.ev_comp);
+        if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+    }
+    if (s_in) cudaStreamDestroy(s_in);
+    if (s_out) cudaStreamDestroy(s_out);
     if (act_arena) cudaFree(act_arena);
     if (w_arena) cudaFree(w_arena);
     if (d_input) cudaFree(d_input);
@@ -413,17 +433,25 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
         if (stem_ok) {
             stem_fused = true;
             const TV tout = e->out_tv[0];
-            const float *w = reinterpret_cast<const float *>(e->w_arena + cw[0].w_f32);
-            const float *bias = reinterpret_cast<const float *>(e->w_arena + cw[0].bias);
-            const int ldw = cw[0].ldw, act = l0.activation, H = l0.h, W = l0.w, nf = l0.n, odt = e->out_dt[0];
+            const int act = l0.activation, H = l0.h, W = l0.w, nf = l0.n, odt = e->out_dt[0];
+            // weights go to the kernel as by-value constants: [27 = (ky,kx,c)][n] + bias
+            StemW<32> w32{}; StemW<16> w16{};
+            for (int f = 0; f < nf; ++f) {
+                for (int c = 0; c < 3; ++c)
+                    for (int t = 0; t < 9; ++t) {
+                        const float v = l0.weights[((size_t)f * 3 + c) * 9 + t];
+                        if (nf == 32) w32.w[(t * 3 + c) * 32 + f] = v; else w16.w[(t * 3 + c) * 16 + f] = v;
+                    }
+                if (nf == 32) w32.b[f] = l0.biases[f]; else w16.b[f] = l0.biases[f];
+            }
             const long total = (long)B * H * W;
             const int grid = (int)((total + 127) / 128);
             e->first_kind = OP_CONV_SIMT; e->first_layer = 0;
             e->first_op = [=](const float *din, cudaStream_t s) {
-                if (nf == 32 && odt == DT_BF16) k_conv_stem<32, __nv_bfloat16><<<grid, 128, 0, s>>>(din, tout, w, ldw, bias, act, H, W);
-                else if (nf == 32) k_conv_stem<32, float><<<grid, 128, 0, s>>>(din, tout, w, ldw, bias, act, H, W);
-                else if (odt == DT_BF16) k_conv_stem<16, __nv_bfloat16><<<grid, 128, 0, s>>>(din, tout, w, ldw, bias, act, H, W);
-                else k_conv_stem<16, float><<<grid, 128, 0, s>>>(din, tout, w, ldw, bias, act, H, W);
+                if (nf == 32 && odt == DT_BF16) k_conv_stem<32, __nv_bfloat16><<<grid, 128, 0, s>>>(din, tout, w32, act, H, W);
+                else if (nf == 32) k_conv_stem<32, float><<<grid, 128, 0, s>>>(din, tout, w32, act, H, W);
+                else if (odt == DT_BF16) k_conv_stem<16, __nv_bfloat16><<<grid, 128, 0, s>>>(din, tout, w16, act, H, W);
+                else k_conv_stem<16, float><<<grid, 128, 0, s>>>(din, tout, w16, act, H, W);
             };
         } else {
             const TV in0 = e->in0;
@@ -631,7 +659,7 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
             need_prev();
             float *dst = e->d_final[i];
             const int classes = l.classes;
-            const int g = grid_for((long)B * l.outputs);
+            const int g = grid_for((long)B * ((l.h * l.w + 31) / 32) * ((l.c + 31) / 32) * 256);
             const int dt = in_dt;
             e->ops.push_back(Op{OP_YOLO, i, [tin, dst, classes, g, dt](cudaStream_t s) {
                 if (dt == DT_F32) k_yolo<float><<<g, 256, 0, s>>>(tin, dst, classes);
@@ -732,6 +760,70 @@ void engine_download_outputs(Engine *e, Network *net, void *stream) {
         net->layers[i].output_count = e->final_count[i];
     }
     CUDA_OK(cudaStreamSynchronize(s));
+}
+
+static void ensure_slots(Engine *e) {
+    if (!e->slots.empty()) return;
+    const int NS = 3;
+    CUDA_OK(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+    e->slots.resize(NS);
+    for (auto &sl : e->slots) {
+        CUDA_OK(cudaMalloc(&sl.d_in, e->input_count * sizeof(float)));
+        sl.d_out.assign(e->d_final.size(), nullptr);
+        sl.h_out.assign(e->d_final.size(), nullptr);
+        for (size_t i = 0; i < e->d_final.size(); ++i) {
+            if (!e->d_final[i]) continue;
+            CUDA_OK(cudaMalloc(&sl.d_out[i], e->final_count[i] * sizeof(float)));
+            CUDA_OK(cudaHostAlloc(&sl.h_out[i], e->final_count[i] * sizeof(float), cudaHostAllocDefault));
+        }
+        CUDA_OK(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&sl.ev_comp, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+    }
+}
+
+// Enqueue one batch: H2D on the copy-in stream, forward on the compute stream, D2H on the copy-out stream.
+// Returns the ticket to pass to engine_collect.  Up to 3 batches may be in flight.
+int engine_submit(Engine *e, const float *host_input) {
+    CUDA_OK(cudaSetDevice(e->opt.device));
+    ensure_slots(e);
+    const int k = e->next_slot;
+    Engine::Slot &sl = e->slots[k];
+    if (sl.busy) fatal_throw("submit: pipeline full (3 batches in flight) -- collect the oldest ticket first");
+    e->next_slot = (k + 1) % (int)e->slots.size();
+    // the previous forward that read d_in[k] must have finished before it is overwritten
+    CUDA_OK(cudaStreamWaitEvent(e->s_in, sl.ev_comp, 0));
+    CUDA_OK(cudaMemcpyAsync(sl.d_in, host_input, e->input_count * sizeof(float), cudaMemcpyHostToDevice, e->s_in));
+    CUDA_OK(cudaEventRecord(sl.ev_in, e->s_in));
+    CUDA_OK(cudaStreamWaitEvent(e->stream, sl.ev_in, 0));
+    engine_forward(e, sl.d_in, e->stream);
+    // the previous D2H out of d_out[k] must have finished before it is overwritten
+    CUDA_OK(cudaStreamWaitEvent(e->stream, sl.ev_done, 0));
+    for (size_t i = 0; i < e->d_final.size(); ++i)
+        if (e->d_final[i])
+            CUDA_OK(cudaMemcpyAsync(sl.d_out[i], e->d_final[i], e->final_count[i] * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+    CUDA_OK(cudaEventRecord(sl.ev_comp, e->stream));
+    CUDA_OK(cudaStreamWaitEvent(e->s_out, sl.ev_comp, 0));
+    for (size_t i = 0; i < e->d_final.size(); ++i)
+        if (e->d_final[i])
+            CUDA_OK(cudaMemcpyAsync(sl.h_out[i], sl.d_out[i], e->final_count[i] * sizeof(float), cudaMemcpyDeviceToHost, e->s_out));
+    CUDA_OK(cudaEventRecord(sl.ev_done, e->s_out));
+    sl.busy = true;
+    return k;
+}
+
+void engine_collect(Engine *e, Network *net, int ticket) {
+    if (ticket < 0 || ticket >= (int)e->slots.size() || !e->slots[ticket].busy) fatal_throw("collect: bad ticket");
+    CUDA_OK(cudaSetDevice(e->opt.device));
+    Engine::Slot &sl = e->slots[ticket];
+    CUDA_OK(cudaEventSynchronize(sl.ev_done));
+    for (size_t i = 0; i < e->d_final.size(); ++i) {
+        if (!e->d_final[i]) continue;
+        net->layers[i].output = sl.h_out[i];
+        net->layers[i].output_count = e->final_count[i];
+    }
+    sl.busy = false;
 }
 
 void engine_fetch_layer(Engine *e, Network *net, int layer, float *dst) {

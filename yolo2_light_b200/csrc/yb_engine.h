@@ -34,6 +34,8 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt);
 void engine_upload_input(Engine *e, const float *host_input, void *stream);
 void engine_forward(Engine *e, const void *d_input, void *stream);
 void engine_download_outputs(Engine *e, Network *net, void *stream);   // async D2H into pinned, then sync
+int engine_submit(Engine *e, const float *host_input);
+void engine_collect(Engine *e, Network *net, int ticket);
 void engine_fetch_layer(Engine *e, Network *net, int layer, float *dst);
 int engine_fetch_counts(Engine *e, int layer, int32_t *dst, size_t count);
 void engine_weight_arena(Engine *e, void **ptr, size_t *bytes);

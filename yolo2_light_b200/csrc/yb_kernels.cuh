@@ -188,14 +188,15 @@ __global__ void __launch_bounds__(256) k_conv_simt(ConvP p) {
 // filters in registers, weights [27][NF] broadcast from shared memory.  Accumulation order (ky, kx, c) matches
 // k_conv_simt.
 // ------------------------------------------------------------------------------------------------------
+template <int NF>
+struct StemW {            // passed by value as a kernel parameter: lives in the constant bank, so every FFMA takes
+    float w[27 * NF];     // its weight operand straight from c[][] -- no shared-memory traffic at all
+    float b[NF];
+};
+
 template <int NF, typename TOut>
-__global__ void __launch_bounds__(128) k_conv_stem(const float *__restrict__ in, TV out, const float *__restrict__ w /*[27][ldw]*/,
-                                                   int ldw, const float *__restrict__ bias, int act, int H, int W) {
-    __shared__ float ws[27 * NF];
-    __shared__ float bs[NF];
-    for (int i = threadIdx.x; i < 27 * NF; i += blockDim.x) ws[i] = w[(i / NF) * ldw + (i % NF)];
-    for (int i = threadIdx.x; i < NF; i += blockDim.x) bs[i] = bias[i];
-    __syncthreads();
+__global__ void __launch_bounds__(128) k_conv_stem(const float *__restrict__ in, TV out, const __grid_constant__ StemW<NF> sw,
+                                                   int act, int H, int W) {
     const long total = (long)out.N * H * W;
     const long p = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (p >= total) return;
@@ -216,15 +217,8 @@ __global__ void __launch_bounds__(128) k_conv_stem(const float *__restrict__ in,
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const float v = ok ? __ldg(img + ((size_t)c * H + iy) * W + ix) : 0.f;
-                const float4 *wp = reinterpret_cast<const float4 *>(ws + ((ky * 3 + kx) * 3 + c) * NF);
 #pragma unroll
-                for (int f4 = 0; f4 < NF / 4; ++f4) {
-                    const float4 wv = wp[f4];
-                    acc[f4 * 4 + 0] = fmaf(v, wv.x, acc[f4 * 4 + 0]);
-                    acc[f4 * 4 + 1] = fmaf(v, wv.y, acc[f4 * 4 + 1]);
-                    acc[f4 * 4 + 2] = fmaf(v, wv.z, acc[f4 * 4 + 2]);
-                    acc[f4 * 4 + 3] = fmaf(v, wv.w, acc[f4 * 4 + 3]);
-                }
+                for (int f = 0; f < NF; ++f) acc[f] = fmaf(v, sw.w[((ky * 3 + kx) * 3 + c) * NF + f], acc[f]);
             }
         }
     }
@@ -236,7 +230,7 @@ __global__ void __launch_bounds__(128) k_conv_stem(const float *__restrict__ in,
             float t[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float a = acc[g * 8 + j] + bs[g * 8 + j];
+                const float a = acc[g * 8 + j] + sw.b[g * 8 + j];
                 t[j] = (act == ACT_LEAKY) ? ((a > 0.f) ? a : 0.1f * a) : act_exact(a, act);
             }
             __nv_bfloat162 h0 = __floats2bfloat162_rn(t[0], t[1]), h1 = __floats2bfloat162_rn(t[2], t[3]);
@@ -248,7 +242,7 @@ __global__ void __launch_bounds__(128) k_conv_stem(const float *__restrict__ in,
         }
     } else {
 #pragma unroll
-        for (int f = 0; f < NF; ++f) o[f] = from_f32<TOut>(act_exact(acc[f] + bs[f], act));
+        for (int f = 0; f < NF; ++f) o[f] = from_f32<TOut>(act_exact(acc[f] + sw.b[f], act));
     }
 }
 
@@ -632,18 +626,40 @@ __global__ void k_reorg(TV in, TV out, int stride) {
 // 4..4+classes of each anchor block.  Reads the head conv's NHWC activation, writes the NCHW f32 tensor the
 // reference decoder expects (additionally.c:4200 entry_index).
 template <typename TIn>
-__global__ void k_yolo(TV in, float *__restrict__ out, int classes) {
-    const long total = (long)in.N * in.C * in.H * in.W;
+__global__ void __launch_bounds__(256) k_yolo(TV in, float *__restrict__ out, int classes) {
+    // 32 pixels x 32 channels per tile: channel-contiguous reads (NHWC), pixel-contiguous writes (NCHW)
+    __shared__ float tile[32][33];
+    const int HW = in.H * in.W;
+    const int ptiles = (HW + 31) / 32, ctiles = (in.C + 31) / 32;
+    const long ntiles = (long)in.N * ptiles * ctiles;
     const int per = 4 + classes + 1;
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int x = (int)(i % in.W);
-        const int y = (int)((i / in.W) % in.H);
-        const int c = (int)((i / ((long)in.W * in.H)) % in.C);
-        const int n = (int)(i / ((long)in.W * in.H * in.C));
-        float v = to_f32(tv_px<TIn>(in, n, y, x)[c]);
-        const int e = c % per;
-        if (e != 2 && e != 3) v = (float)(1.0 / (1.0 + exp(-(double)v)));
-        out[i] = v;
+    const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;   // 8 warps
+    for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int ct = (int)(t % ctiles);
+        const int pt = (int)((t / ctiles) % ptiles);
+        const int n = (int)(t / ((long)ctiles * ptiles));
+        const int c = ct * 32 + lane;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int pl = wy * 4 + k;
+            const int hw = pt * 32 + pl;
+            float v = 0.f;
+            if (hw < HW && c < in.C) {
+                v = to_f32(tv_px<TIn>(in, n, hw / in.W, hw % in.W)[c]);
+                const int e = c % per;
+                if (e != 2 && e != 3) v = (float)(1.0 / (1.0 + exp(-(double)v)));
+            }
+            tile[pl][lane] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int cl = wy * 4 + k;
+            const int cc = ct * 32 + cl;
+            const int hw = pt * 32 + lane;
+            if (hw < HW && cc < in.C) out[((size_t)n * in.C + cc) * HW + hw] = tile[lane][cl];
+        }
+        __syncthreads();
     }
 }
 
