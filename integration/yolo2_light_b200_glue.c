@@ -1,0 +1,92 @@
+/*
+ * yolo2_light_b200_glue.c -- the reference-side binding a yolo2_light maintainer would add.
+ *
+ * Compiled TOGETHER WITH the reference's own sources (it includes the reference's src/additionally.h) and linked
+ * against libyolo2_light_b200.so.  It adds two functions with exactly the shape of the reference's accelerator
+ * slots (src/additionally.h:953-959, network_predict_gpu_cudnn / network_predict_gpu_cudnn_quantized):
+ *
+ *     float *network_predict_b200(network net, float *input);
+ *     float *network_predict_b200_quantized(network net, float *input);
+ *
+ * Call sites to switch: src/main.c:199-219, src/main.c:394-414, src/additionally.c:4639-4659.
+ * Preconditions are the reference's own (main.c:160-171): parse_network_cfg, load_weights_upto_cpu,
+ * yolov2_fuse_conv_batchnorm, calculate_binary_weights, [quantinization_and_get_multipliers].
+ *
+ * On the first call the prepared per-layer arrays of `net` are handed to the engine as yb_layer_desc[]
+ * (snapshot after preparation); afterwards each call is H2D + CUDA graph + D2H.  The activated
+ * YOLO/REGION tensors are copied into the reference layers' host l.output, so get_network_boxes / do_nms_sort /
+ * draw_detections_v3 keep working unchanged.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "additionally.h"
+#include "yolo2_light_b200.h"
+
+#define YB_GLUE_MAX_NETS 8
+static struct { layer *key; int quantized; yb_network *h; } g_nets[YB_GLUE_MAX_NETS];
+
+static yb_network *glue_build(network net, int quantized)
+{
+    yb_layer_desc *d = (yb_layer_desc *)calloc(net.n, sizeof(yb_layer_desc));
+    int i;
+    for (i = 0; i < net.n; ++i) {
+        layer *l = &net.layers[i];
+        d[i].type = (int)l->type;               /* same numeric values as LAYER_TYPE */
+        d[i].activation = (int)l->activation;   /* same numeric values as ACTIVATION */
+        d[i].batch_normalize = l->batch_normalize;
+        d[i].h = l->h; d[i].w = l->w; d[i].c = l->c; d[i].n = l->n;
+        d[i].size = l->size; d[i].stride = l->stride; d[i].pad = l->pad;
+        d[i].out_h = l->out_h; d[i].out_w = l->out_w; d[i].out_c = l->out_c;
+        d[i].xnor = l->xnor; d[i].quantized = l->quantized; d[i].index = l->index;
+        d[i].classes = l->classes; d[i].coords = l->coords; d[i].softmax = l->softmax; d[i].total = l->total;
+        d[i].reverse = l->reverse; d[i].scale = l->scale;
+        d[i].input_layers = l->input_layers; d[i].mask = l->mask;
+        if (l->type == CONVOLUTIONAL) {
+            d[i].weights = l->weights; d[i].biases = l->biases;
+            d[i].scales = l->scales; d[i].rolling_mean = l->rolling_mean; d[i].rolling_variance = l->rolling_variance;
+            if (quantized) {
+                d[i].weights_int8 = l->weights_int8;
+                d[i].weights_quant_multipler = l->weights_quant_multipler;
+                d[i].input_quant_multipler = l->input_quant_multipler;
+            }
+            d[i].mean_arr = l->xnor ? l->mean_arr : NULL;
+        } else if (l->type == YOLO || l->type == REGION) {
+            d[i].anchors = l->biases;
+        }
+    }
+    yb_network *h = yb_network_from_layers(d, net.n, net.batch, net.h, net.w, net.c, quantized);
+    free(d);
+    if (h && net.gpu_index >= 0) yb_network_set_device(h, net.gpu_index);
+    return h;
+}
+
+static float *glue_predict(network net, float *input, int quantized)
+{
+    int k, i;
+    yb_network *h = NULL;
+    for (k = 0; k < YB_GLUE_MAX_NETS; ++k)
+        if (g_nets[k].h && g_nets[k].key == net.layers && g_nets[k].quantized == quantized) h = g_nets[k].h;
+    if (!h) {
+        h = glue_build(net, quantized);
+        for (k = 0; k < YB_GLUE_MAX_NETS; ++k)
+            if (!g_nets[k].h) { g_nets[k].key = net.layers; g_nets[k].quantized = quantized; g_nets[k].h = h; break; }
+    }
+    if (quantized) yb_network_predict_quantized(h, input);
+    else yb_network_predict(h, input);
+    /* what get_network_boxes reads (additionally.c:4391-4398): host l.output of every YOLO / REGION layer */
+    for (i = 0; i < net.n; ++i) {
+        layer *l = &net.layers[i];
+        if (l->type == YOLO || l->type == REGION || i == net.n - 1) {
+            int count = 0;
+            const float *src = yb_network_layer_output(h, i, &count);
+            if (src && l->output) memcpy(l->output, src, sizeof(float) * (size_t)count);
+        }
+    }
+    for (i = net.n - 1; i > 0; --i) if (net.layers[i].type != COST) break;   /* as network_predict_cpu returns */
+    return net.layers[i].output;
+}
+
+float *network_predict_b200(network net, float *input) { return glue_predict(net, input, 0); }
+float *network_predict_b200_quantized(network net, float *input) { return glue_predict(net, input, 1); }

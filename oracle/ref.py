@@ -59,6 +59,9 @@ def _load(kind: str):
     lib.refh_get_boxes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_int,
                                    C.POINTER(C.c_int)]
     lib.refh_set_quiet.argtypes = [C.c_int]
+    if hasattr(lib, "refh_predict_b200"):
+        lib.refh_predict_b200.restype = C.POINTER(C.c_float)
+        lib.refh_predict_b200.argtypes = [C.c_void_p, C.c_void_p]
     _libs[kind] = lib
     return lib
 
@@ -113,6 +116,12 @@ class RefNet:
         x = np.ascontiguousarray(x, dtype=np.float32)
         assert x.size == self.inputs * self.batch, (x.shape, self.inputs, self.batch)
         self.lib.refh_predict(self.h, x.ctypes.data_as(C.c_void_p))
+        return self.output(self.n - 1)
+
+    def predict_b200(self, x: np.ndarray) -> np.ndarray:
+        """network_predict_b200 of integration/yolo2_light_b200_glue.c (kind='dropin' only)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        self.lib.refh_predict_b200(self.h, x.ctypes.data_as(C.c_void_p))
         return self.output(self.n - 1)
 
     def forward_layer(self, i: int, x: np.ndarray, use_q_rule: Optional[bool] = None) -> np.ndarray:

@@ -222,3 +222,13 @@ void refh_im2col(float *im, int c, int hgt, int w, int k, int stride, int pad, f
 {
     im2col_cpu(im, c, hgt, w, k, stride, pad, col);   /* additionally.c:39 */
 }
+
+#ifdef YB_DROPIN
+/* drop-in check: the glue of integration/yolo2_light_b200_glue.c behind the reference's own host code */
+float *network_predict_b200(network net, float *input);
+float *network_predict_b200_quantized(network net, float *input);
+float *refh_predict_b200(refh *h, float *input)
+{
+    return h->quantized ? network_predict_b200_quantized(h->net, input) : network_predict_b200(h->net, input);
+}
+#endif

@@ -255,3 +255,26 @@ def test_empty_and_edge_inputs(workdir):
                 assert util.rel_l2(o, outs[i].reshape(o.shape)) <= 1e-5
     with pytest.raises(yb.YbError):
         net.predict(np.zeros((1, 3, 8, 8), np.float32))
+
+
+@pytest.mark.skipif(not __import__("oracle.ref", fromlist=["x"]).available("dropin"), reason="drop-in build absent")
+@pytest.mark.parametrize("name,q", [("tiny64", 0), ("tiny64", 1), ("xnor64", 0), ("v3_32", 0)])
+def test_true_dropin_behind_reference_host_code(name, q, workdir):
+    """oracle/_ref/libyolo2ref_dropin.so = the reference's UNMODIFIED host code (parser, loader, BN fold, binary
+    weights, quantisation, get_network_boxes, do_nms_sort) + integration/yolo2_light_b200_glue.c + our engine:
+    network_predict_b200(net, input) in the slot of network_predict_cpu; detections through the reference's own
+    decoder must agree with its CPU path."""
+    from oracle import ref
+    cfg, wts = util.model_files(name, workdir)
+    x = util.images(name, 1)
+    net = ref.RefNet(cfg, wts, 1, q, 7, kind="dropin")
+    net.predict(x)                                   # reference CPU forward
+    det_idx = [i for i, L in enumerate(net.layers) if L["type_name"] in ("YOLO", "REGION")]
+    cpu_out = {i: net.output(i).copy() for i in det_idx}
+    cpu_boxes = net.get_boxes(640, 480, 0.25, 0.45)
+    net.predict_b200(x)                              # same `network`, forward on the B200
+    tol = 3e-3
+    for i in det_idx:
+        assert util.rel_l2(net.output(i), cpu_out[i]) <= tol, (name, q, i)
+    gpu_boxes = net.get_boxes(640, 480, 0.25, 0.45)
+    assert abs(gpu_boxes.shape[0] - cpu_boxes.shape[0]) <= max(2, cpu_boxes.shape[0] // 50)
