@@ -193,10 +193,9 @@ def main():
     net.set_device(local_rank)
     ptr, nbytes = net.weight_arena(quantized=bool(q), upload=(rank == 0))
     if world > 1:
-        class _Arena:   # zero-copy torch view of the engine's weight arena
-            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-        arena = torch.as_tensor(_Arena(), device=torch.device("cuda", local_rank))
-        dist.broadcast(arena, src=0)          # the ONLY collective of the whole job (NCCL over NVLink)
+        from yolo2_light_b200 import parallel
+        arena = parallel.arena_tensor(ptr, nbytes, torch.device("cuda", local_rank))   # zero-copy view of the engine's arena
+        parallel.broadcast_arena(arena, src=0)   # the ONLY collective of the whole job (NCCL over NVLink)
         torch.cuda.synchronize()
 
     # ---- inputs resident in HBM: 4 rotating batches (> L2 together with ~4 GB of activations per step) ----
