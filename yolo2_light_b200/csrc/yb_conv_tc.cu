@@ -47,7 +47,8 @@ struct TcParams {
     int stride2;
     int xoff, yoff;
     int stages;
-    uint32_t stage_bytes, a_bytes;
+    uint32_t stage_bytes, a_bytes, b_bytes;   // per stage (all sub-blocks); per K-block A tile; per K-block B tile
+    int sps;                                  // K-blocks per pipeline stage (amortises the per-stage barrier round trip)
     uint32_t idesc, desc_hi;  // UMMA instruction descriptor; high word of the smem descriptors
     char *out; long out_ldc; int out_bf16; int n, n_store;
     const char *res; long res_ldc; int res_bf16;
@@ -186,17 +187,22 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 const int x0 = (m % p.xt) * p.TW;
                 const int J0 = (m / p.xt) * p.TH;
                 const int n0 = n_idx * p.BN;
-                for (int kb = 0; kb < p.kblocks; ++kb) {
-                    const int tap = kb / p.cblocks;
-                    const int c0 = (kb - tap * p.cblocks) * p.BK;
-                    const int ky = tap / p.size, kx = tap - ky * p.size;
+                for (int kb0 = 0; kb0 < p.kblocks; kb0 += p.sps) {
+                    const int nsub = min(p.sps, p.kblocks - kb0);
                     mbar_wait(empty_bar(stage), phase ^ 1u, 0);
                     const uint32_t a_dst = smem0 + (uint32_t)stage * p.stage_bytes;
-                    const uint32_t b_dst = a_dst + p.a_bytes;
-                    mbar_arrive_expect_tx(full_bar(stage), p.stage_bytes);
-                    if (p.stride2) tma_load_5d(a_dst, &tmA, full_bar(stage), c0, kx & 1, x0 + (kx >> 1), ky & 1, J0 + (ky >> 1));
-                    else tma_load_3d(a_dst, &tmA, full_bar(stage), c0, x0 + kx + p.xoff, J0 + ky + p.yoff);
-                    tma_load_2d(b_dst, &tmB, full_bar(stage), kb * p.BK, n0);
+                    const uint32_t b_dst = a_dst + (uint32_t)p.sps * p.a_bytes;
+                    mbar_arrive_expect_tx(full_bar(stage), (uint32_t)nsub * (p.a_bytes + p.b_bytes));
+                    for (int j = 0; j < nsub; ++j) {
+                        const int kb = kb0 + j;
+                        const int tap = kb / p.cblocks;
+                        const int c0 = (kb - tap * p.cblocks) * p.BK;
+                        const int ky = tap / p.size, kx = tap - ky * p.size;
+                        const uint32_t ad = a_dst + (uint32_t)j * p.a_bytes, bd = b_dst + (uint32_t)j * p.b_bytes;
+                        if (p.stride2) tma_load_5d(ad, &tmA, full_bar(stage), c0, kx & 1, x0 + (kx >> 1), ky & 1, J0 + (ky >> 1));
+                        else tma_load_3d(ad, &tmA, full_bar(stage), c0, x0 + kx + p.xoff, J0 + ky + p.yoff);
+                        tma_load_2d(bd, &tmB, full_bar(stage), kb * p.BK, n0);
+                    }
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -211,17 +217,21 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 1);   // epilogue drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
-                for (int kb = 0; kb < p.kblocks; ++kb) {
+                for (int kb0 = 0; kb0 < p.kblocks; kb0 += p.sps) {
+                    const int nsub = min(p.sps, p.kblocks - kb0);
                     mbar_wait(full_bar(stage), phase, 2);        // TMA bytes have landed
                     tc_fence_after();
-                    const uint32_t a_addr = smem0 + (uint32_t)stage * p.stage_bytes;
-                    const uint32_t b_addr = a_addr + p.a_bytes;
+                    const uint32_t a_base = smem0 + (uint32_t)stage * p.stage_bytes;
+                    const uint32_t b_base = a_base + (uint32_t)p.sps * p.a_bytes;
                     const uint64_t hi = (uint64_t)p.desc_hi << 32;
-                    for (int k = 0; k < kk; ++k) {
-                        // K-major operand, K advance of 16 bf16 = 32 bytes inside the swizzle row
-                        const uint64_t adesc = hi | (uint64_t)((((a_addr + 32u * k) & 0x3FFFFu) >> 4) | (1u << 16));
-                        const uint64_t bdesc = hi | (uint64_t)((((b_addr + 32u * k) & 0x3FFFFu) >> 4) | (1u << 16));
-                        umma_bf16(d_tmem, adesc, bdesc, p.idesc, (uint32_t)((kb | k) != 0));
+                    for (int j = 0; j < nsub; ++j) {
+                        const uint32_t a_addr = a_base + (uint32_t)j * p.a_bytes, b_addr = b_base + (uint32_t)j * p.b_bytes;
+                        for (int k = 0; k < kk; ++k) {
+                            // K-major operand, K advance of 16 bf16 = 32 bytes inside the swizzle row
+                            const uint64_t adesc = hi | (uint64_t)((((a_addr + 32u * k) & 0x3FFFFu) >> 4) | (1u << 16));
+                            const uint64_t bdesc = hi | (uint64_t)((((b_addr + 32u * k) & 0x3FFFFu) >> 4) | (1u << 16));
+                            umma_bf16(d_tmem, adesc, bdesc, p.idesc, (uint32_t)((kb0 | j | k) != 0));
+                        }
                     }
                     umma_commit(empty_bar(stage));               // frees the smem stage when these MMAs retire
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -424,8 +434,13 @@ void *tc_make_plan(const Layer &l, const TV &in, const TV &out, bool out_bf16, c
     p.nt = (l.n + BN - 1) / BN;
     p.num_tiles = p.xt * p.jt * p.nt;
     p.a_bytes = (uint32_t)(TC_BM * BK * 2);
-    p.stage_bytes = p.a_bytes + (uint32_t)(BN * BK * 2);
+    p.b_bytes = (uint32_t)(BN * BK * 2);
     p.nt = (l.n + BN - 1) / BN;
+    // several K-blocks per stage when they are small: the single MMA-issuing thread pays a fixed barrier round
+    // trip per stage, which dominated the C<=64 layers (profiles/r01_notes.md)
+    p.sps = (int)std::max<uint32_t>(1, std::min<uint32_t>(4, (64u * 1024u) / (p.a_bytes + p.b_bytes)));
+    p.sps = std::min(p.sps, p.kblocks);
+    p.stage_bytes = (uint32_t)p.sps * (p.a_bytes + p.b_bytes);
     p.stages = (int)std::min<size_t>(8, (200 * 1024 - sizeof(float) * (size_t)p.nt * BN) / p.stage_bytes);
     if (p.stages < 2) fatal_throw("tc plan: tile does not fit shared memory");
     // UMMA instruction descriptor (kind::f16): D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24

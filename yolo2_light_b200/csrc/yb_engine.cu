@@ -590,8 +590,13 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
             const int stride = l.stride; const float scale = l.scale;
             const int g = grid_for((long)B * l.out_h * l.out_w * l.out_c);
             const int dt = in_dt;
-            e->ops.push_back(Op{OP_UPSAMPLE, i, [tin, tout, stride, scale, g, dt](cudaStream_t s) {
-                if (dt == DT_F32) k_upsample<float><<<g, 256, 0, s>>>(tin, tout, stride, scale);
+            const int esz = (int)dt_size(dt);
+            const bool vec = scale == 1.f && (l.out_c * esz) % 16 == 0 && (tin.ldc * esz) % 16 == 0 && (tout.ldc * esz) % 16 == 0 &&
+                             (reinterpret_cast<uintptr_t>(tin.base) & 15) == 0 && (reinterpret_cast<uintptr_t>(tout.base) & 15) == 0;
+            const int gv = grid_for((long)B * l.out_h * l.out_w * ((l.out_c * esz) / 16 + 1));
+            e->ops.push_back(Op{OP_UPSAMPLE, i, [tin, tout, stride, scale, g, dt, vec, gv, esz](cudaStream_t s) {
+                if (vec) k_upsample_vec16<<<gv, 256, 0, s>>>(tin, tout, stride, esz);
+                else if (dt == DT_F32) k_upsample<float><<<g, 256, 0, s>>>(tin, tout, stride, scale);
                 else k_upsample<__nv_bfloat16><<<g, 256, 0, s>>>(tin, tout, stride, scale);
             }});
             break;
@@ -661,9 +666,10 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
             const int classes = l.classes;
             const int g = grid_for((long)B * ((l.h * l.w + 31) / 32) * ((l.c + 31) / 32) * 256);
             const int dt = in_dt;
-            e->ops.push_back(Op{OP_YOLO, i, [tin, dst, classes, g, dt](cudaStream_t s) {
-                if (dt == DT_F32) k_yolo<float><<<g, 256, 0, s>>>(tin, dst, classes);
-                else k_yolo<__nv_bfloat16><<<g, 256, 0, s>>>(tin, dst, classes);
+            const int fast = (ADT == DT_BF16) ? 1 : 0;
+            e->ops.push_back(Op{OP_YOLO, i, [tin, dst, classes, g, dt, fast](cudaStream_t s) {
+                if (dt == DT_F32) k_yolo<float><<<g, 256, 0, s>>>(tin, dst, classes, fast);
+                else k_yolo<__nv_bfloat16><<<g, 256, 0, s>>>(tin, dst, classes, fast);
             }});
             break;
         }

@@ -563,6 +563,22 @@ __global__ void k_upsample(TV in, TV out, int stride, float scale) {
     }
 }
 
+// same, 16 bytes per thread (scale == 1: a pure copy of bits, exact for any dtype)
+static __global__ void k_upsample_vec16(TV in, TV out, int stride, int esize) {
+    const int chunks = (out.C * esize) >> 4;
+    const long total = (long)out.N * out.H * out.W * chunks;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % chunks);
+        const long pxl = i / chunks;
+        const int x = (int)(pxl % out.W);
+        const int y = (int)((pxl / out.W) % out.H);
+        const int n = (int)(pxl / ((long)out.W * out.H));
+        const char *src = in.base + (((size_t)(n * in.Hp + y / stride + in.P) * in.Wp + (x / stride + in.P)) * (size_t)in.ldc) * esize;
+        char *dst = out.base + (((size_t)(n * out.Hp + y + out.P) * out.Wp + (x + out.P)) * (size_t)out.ldc) * esize;
+        reinterpret_cast<uint4 *>(dst)[ch] = __ldg(reinterpret_cast<const uint4 *>(src) + ch);
+    }
+}
+
 // forward_shortcut_layer_cpu (reference yolov2_forward_network.c:443-449, shortcut_cpu :410-432):
 // out = act(in + from) with the general stride/sample subsampling of shortcut_cpu.
 template <typename T>
@@ -626,7 +642,7 @@ __global__ void k_reorg(TV in, TV out, int stride) {
 // 4..4+classes of each anchor block.  Reads the head conv's NHWC activation, writes the NCHW f32 tensor the
 // reference decoder expects (additionally.c:4200 entry_index).
 template <typename TIn>
-__global__ void __launch_bounds__(256) k_yolo(TV in, float *__restrict__ out, int classes) {
+__global__ void __launch_bounds__(256) k_yolo(TV in, float *__restrict__ out, int classes, int fast) {
     // 32 pixels x 32 channels per tile: channel-contiguous reads (NHWC), pixel-contiguous writes (NCHW)
     __shared__ float tile[32][33];
     const int HW = in.H * in.W;
@@ -647,7 +663,9 @@ __global__ void __launch_bounds__(256) k_yolo(TV in, float *__restrict__ out, in
             if (hw < HW && c < in.C) {
                 v = to_f32(tv_px<TIn>(in, n, hw / in.W, hw % in.W)[c]);
                 const int e = c % per;
-                if (e != 2 && e != 3) v = (float)(1.0 / (1.0 + exp(-(double)v)));
+                // exact nets: the reference's double-precision logistic; bf16 tensor-core nets: f32 (error ~1e-7,
+                // far below the path's 1e-3 bar)
+                if (e != 2 && e != 3) v = fast ? 1.f / (1.f + __expf(-v)) : (float)(1.0 / (1.0 + exp(-(double)v)));
             }
             tile[pl][lane] = v;
         }
