@@ -16,14 +16,17 @@
 //   * 4 epilogue warps read TMEM (tcgen05.ld 32x32b.x32), add bias (folded batch-norm), apply leaky-ReLU, add the
 //     shortcut residual when fused (reference :443-449), and store bf16 (or f32 for detection heads) NHWC.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue
+// (two warps per TMEM lane quarter, each owning half of the accumulator columns).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "yb_conv_tc.cuh"
 
@@ -32,7 +35,8 @@ namespace yb {
 namespace {
 
 constexpr int TC_BM = 128;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;              // two warps per TMEM lane quarter, each takes half of the columns
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_ACC = 2;   // TMEM accumulator stages
 
 struct TcParams {
@@ -40,6 +44,8 @@ struct TcParams {
     int TW, TWlog2, TH;       // tile = TW x TH output pixels (TW*TH == 128)
     int xt, jt, nt;           // #tiles along x, merged rows, filters
     int num_tiles;
+    int num_work;             // work items of the persistent loop: num_tiles (CG=1) or pairs of m-tiles x nt (CG=2)
+    int cg;                   // 1, or 2 = CTA pairs (cta_group::2)
     int PR, row_off;          // merged-row pitch per image; output row = (J % PR) - row_off
     int OH, OW, OHp, OWp;
     int size, cblocks, kblocks;
@@ -54,6 +60,9 @@ struct TcParams {
     const char *res; long res_ldc; int res_bf16;
     const float *bias; int act, act2;
     uint32_t tmem_cols;
+    unsigned long long *stats; // YB_TC_STATS=1: per-CTA cycle counters [grid][8] (diagnostic)
+    int no_coalesce;          // YB_TC_NO_COALESCE=1: per-thread row stores (the pre-staging epilogue), for A/B comparison
+    int dbg;                  // YB_TC_DBG bit mask for bottleneck experiments: 1 no TMA, 2 no MMA, 4 no epilogue memory ops
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -143,6 +152,50 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
+// --- cluster helpers (CG == 2: a CTA pair, tcgen05 cta_group::2) --------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {   // arrive on the same barrier of CTA `cta`
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(bar), "r"(cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-pair rank bit of a shared::cluster address -> leader CTA
+__device__ __forceinline__ void tma2_load_3d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma2_load_5d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2,
+                                             int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_both(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+// CG = 1: one CTA per 128-pixel tile.  CG = 2: a CTA pair computes a 256-pixel x BN tile with cta_group::2 MMAs --
+// each CTA loads its own 128 pixels of A and HALF of the B (filter) tile, so the bytes every SM pulls through its
+// TMA unit per FLOP drop by a third; that unit (~64 B/clk/SM) is what bounds the BN=256 layers
+// (profiles/r01_notes.md).  The leader CTA (cluster rank 0) issues the MMAs for both.
+template <int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -156,109 +209,160 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    // work items: CG=1 -> (m_tile, n_tile); CG=2 -> (pair of m_tiles, n_tile), both CTAs of a pair iterate in lockstep
+    const int w_first = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int w_step = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0 && elect_one()) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        // full: one arrival (the leader's expect_tx; the peer's bytes are covered by the transaction count);
+        // tempty: one arrival per epilogue warp (of both CTAs when paired)
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < TC_ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+        for (int a = 0; a < TC_ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), CG * TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     // bias (folded batch-norm) for all filter tiles -> shared memory, once per CTA
     float *bias_s = reinterpret_cast<float *>(smem_raw + (tmem_slot + 16u - smem_u32(smem_raw)));
+    // 4 KB of staging per epilogue warp (32 rows x 128 B, XOR-swizzled) for the coalescing transposes
+    const uint32_t stg_base = ((tmem_slot + 16u + 4u * (uint32_t)(p.nt * p.BN)) + 127u) & ~127u;
     for (int i = threadIdx.x; i < p.nt * p.BN; i += TC_THREADS) bias_s[i] = (i < p.n) ? __ldg(p.bias + i) : 0.f;
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
     if (warp == 0) {
-        // ======================= TMA producer =======================
+        // ======================= TMA producer (every CTA loads its own A rows and its share of B) ===========
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
-            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-                const int n_idx = t % p.nt;
-                const int m = t / p.nt;
-                const int x0 = (m % p.xt) * p.TW;
-                const int J0 = (m / p.xt) * p.TH;
-                const int n0 = n_idx * p.BN;
-                for (int kb0 = 0; kb0 < p.kblocks; kb0 += p.sps) {
-                    const int nsub = min(p.sps, p.kblocks - kb0);
-                    mbar_wait(empty_bar(stage), phase ^ 1u, 0);
-                    const uint32_t a_dst = smem0 + (uint32_t)stage * p.stage_bytes;
-                    const uint32_t b_dst = a_dst + (uint32_t)p.sps * p.a_bytes;
-                    mbar_arrive_expect_tx(full_bar(stage), (uint32_t)nsub * (p.a_bytes + p.b_bytes));
-                    for (int j = 0; j < nsub; ++j) {
-                        const int kb = kb0 + j;
-                        const int tap = kb / p.cblocks;
-                        const int c0 = (kb - tap * p.cblocks) * p.BK;
-                        const int ky = tap / p.size, kx = tap - ky * p.size;
-                        const uint32_t ad = a_dst + (uint32_t)j * p.a_bytes, bd = b_dst + (uint32_t)j * p.b_bytes;
-                        if (p.stride2) tma_load_5d(ad, &tmA, full_bar(stage), c0, kx & 1, x0 + (kx >> 1), ky & 1, J0 + (ky >> 1));
-                        else tma_load_3d(ad, &tmA, full_bar(stage), c0, x0 + kx + p.xoff, J0 + ky + p.yoff);
-                        tma_load_2d(bd, &tmB, full_bar(stage), kb * p.BK, n0);
+            long long w_empty = 0, w_tma = 0; const long long t_begin = clock64();
+            // loop-invariant parameters in registers; the (tap, channel-block) walk is incremental -- the first version
+            // recomputed it with two integer divisions per K-block, and that ~700-cycle dependent scalar chain in
+            // this single thread was what starved the tensor pipe (profiles/r01_notes.md)
+            const int sps = p.sps, kblocks = p.kblocks, cblocks = p.cblocks, BK = p.BK, fsize = p.size, stages = p.stages;
+            const int xoff = p.xoff, yoff = p.yoff, stride2 = p.stride2, nt = p.nt, xt = p.xt;
+            const uint32_t a_bytes = p.a_bytes, b_bytes = p.b_bytes, stage_bytes = p.stage_bytes;
+            const uint32_t b_off = (uint32_t)sps * a_bytes;
+            for (int w = w_first; w < p.num_work; w += w_step) {
+                const int n_idx = w % nt;
+                const int m = (CG == 2) ? 2 * (w / nt) + (int)rank : w / nt;
+                const int x0 = (m % xt) * p.TW;
+                const int J0 = (m / xt) * p.TH;
+                const int n0 = n_idx * p.BN + (int)rank * (p.BN / CG);
+                int cb = 0, kx = 0, ky = 0, kcol = 0;   // channel block, tap x/y, K column of the weight matrix
+                for (int kb0 = 0; kb0 < kblocks; kb0 += sps) {
+                    const int nsub = min(sps, kblocks - kb0);
+                    { const long long c0 = clock64(); mbar_wait(empty_bar(stage), phase ^ 1u, 0); w_empty += clock64() - c0; }
+                    const uint32_t fb = full_bar(stage);
+                    const uint32_t a_dst = smem0 + (uint32_t)stage * stage_bytes;
+                    const uint32_t b_dst = a_dst + b_off;
+                    if (p.dbg & 1) {
+                        if (leader) mbar_arrive(fb);
+                        if (++stage == stages) { stage = 0; phase ^= 1u; }
+                        continue;
                     }
-                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                    // the leader's barrier collects the bytes of BOTH CTAs (the 2-CTA TMA form signals the leader)
+                    if (leader) mbar_arrive_expect_tx(fb, (uint32_t)(CG * nsub) * (a_bytes + b_bytes));
+                    const long long ct0 = clock64();
+                    for (int j = 0; j < nsub; ++j) {
+                        const uint32_t ad = a_dst + (uint32_t)j * a_bytes, bd = b_dst + (uint32_t)j * b_bytes;
+                        const int c0 = cb * BK;
+                        if constexpr (CG == 2) {
+                            if (stride2) tma2_load_5d(ad, &tmA, fb, c0, kx & 1, x0 + (kx >> 1), ky & 1, J0 + (ky >> 1));
+                            else tma2_load_3d(ad, &tmA, fb, c0, x0 + kx + xoff, J0 + ky + yoff);
+                            tma2_load_2d(bd, &tmB, fb, kcol, n0);
+                        } else {
+                            if (stride2) tma_load_5d(ad, &tmA, fb, c0, kx & 1, x0 + (kx >> 1), ky & 1, J0 + (ky >> 1));
+                            else tma_load_3d(ad, &tmA, fb, c0, x0 + kx + xoff, J0 + ky + yoff);
+                            tma_load_2d(bd, &tmB, fb, kcol, n0);
+                        }
+                        kcol += BK;
+                        if (++cb == cblocks) { cb = 0; if (++kx == fsize) { kx = 0; ++ky; } }
+                    }
+                    w_tma += clock64() - ct0;
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
                 }
             }
+            if (p.stats) { p.stats[blockIdx.x * 8 + 0] = (unsigned long long)w_empty; p.stats[blockIdx.x * 8 + 1] = (unsigned long long)(clock64() - t_begin); p.stats[blockIdx.x * 8 + 7] = (unsigned long long)w_tma; }
         }
     } else if (warp == 1) {
-        // ======================= MMA issuer =======================
-        if (elect_one()) {
+        // ======================= MMA issuer (CG=2: the leader CTA only, for both CTAs) =======================
+        if (leader && elect_one()) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            const int kk = p.BK / 16;
-            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 1);   // epilogue drained this accumulator
+            const int kk = p.BK / 16, sps = p.sps, kblocks = p.kblocks, stages = p.stages, BN = p.BN;
+            const uint32_t a_bytes = p.a_bytes, b_bytes = p.b_bytes, stage_bytes = p.stage_bytes, idesc = p.idesc, dbg = (uint32_t)p.dbg;
+            const uint32_t b_off = (uint32_t)sps * a_bytes;
+            const uint64_t hi = (uint64_t)p.desc_hi << 32;
+            long long w_full = 0, w_tempty = 0; const long long t_begin = clock64();
+            for (int w = w_first; w < p.num_work; w += w_step) {
+                { const long long c0 = clock64(); mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 1); w_tempty += clock64() - c0; }   // epilogue(s) drained this accumulator
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
-                for (int kb0 = 0; kb0 < p.kblocks; kb0 += p.sps) {
-                    const int nsub = min(p.sps, p.kblocks - kb0);
-                    mbar_wait(full_bar(stage), phase, 2);        // TMA bytes have landed
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb0 = 0; kb0 < kblocks; kb0 += sps) {
+                    const int nsub = min(sps, kblocks - kb0);
+                    { const long long c0 = clock64(); mbar_wait(full_bar(stage), phase, 2); w_full += clock64() - c0; }   // TMA bytes have landed
                     tc_fence_after();
-                    const uint32_t a_base = smem0 + (uint32_t)stage * p.stage_bytes;
-                    const uint32_t b_base = a_base + (uint32_t)p.sps * p.a_bytes;
-                    const uint64_t hi = (uint64_t)p.desc_hi << 32;
-                    for (int j = 0; j < nsub; ++j) {
-                        const uint32_t a_addr = a_base + (uint32_t)j * p.a_bytes, b_addr = b_base + (uint32_t)j * p.b_bytes;
+                    const uint32_t a_base = smem0 + (uint32_t)stage * stage_bytes;
+                    const uint32_t b_base = a_base + b_off;
+                    for (int j = 0; j < nsub && !(dbg & 2); ++j) {
+                        // K-major operands; K advance of 16 bf16 = 32 bytes inside the swizzle row = +2 in the
+                        // descriptor's 16-byte address units
+                        uint64_t adesc = hi | (uint64_t)((((a_base + (uint32_t)j * a_bytes) & 0x3FFFFu) >> 4) | (1u << 16));
+                        uint64_t bdesc = hi | (uint64_t)((((b_base + (uint32_t)j * b_bytes) & 0x3FFFFu) >> 4) | (1u << 16));
                         for (int k = 0; k < kk; ++k) {
-                            // K-major operand, K advance of 16 bf16 = 32 bytes inside the swizzle row
-                            const uint64_t adesc = hi | (uint64_t)((((a_addr + 32u * k) & 0x3FFFFu) >> 4) | (1u << 16));
-                            const uint64_t bdesc = hi | (uint64_t)((((b_addr + 32u * k) & 0x3FFFFu) >> 4) | (1u << 16));
-                            umma_bf16(d_tmem, adesc, bdesc, p.idesc, (uint32_t)((kb0 | j | k) != 0));
+                            if constexpr (CG == 2) umma2_bf16(d_tmem, adesc, bdesc, idesc, (uint32_t)((kb0 | j | k) != 0));
+                            else umma_bf16(d_tmem, adesc, bdesc, idesc, (uint32_t)((kb0 | j | k) != 0));
+                            adesc += 2; bdesc += 2;
                         }
                     }
-                    umma_commit(empty_bar(stage));               // frees the smem stage when these MMAs retire
-                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                    // frees the smem stage (in both CTAs) when these MMAs retire
+                    if constexpr (CG == 2) umma2_commit_both(empty_bar(stage)); else umma_commit(empty_bar(stage));
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(tfull_bar(acc));                     // accumulator complete -> epilogue
+                // accumulator complete -> epilogue warps (of both CTAs)
+                if constexpr (CG == 2) umma2_commit_both(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
                 if (++acc == TC_ACC) { acc = 0; acc_phase ^= 1u; }
             }
+            if (p.stats) { p.stats[blockIdx.x * 8 + 2] = (unsigned long long)w_full; p.stats[blockIdx.x * 8 + 3] = (unsigned long long)w_tempty;
+                           p.stats[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_begin); }
         }
     } else {
-        // ======================= epilogue (warps 2..5) =======================
+        // ======================= epilogue (warps 2..9) =======================
         // Per 64-column slab: issue both TMEM loads and the residual loads first, wait once, then do the math and
         // the stores -- global-load latency is paid once per slab instead of once per value (the first version
         // was epilogue-bound on exactly that, profiles/r01_notes.md).
         const int q = warp & 3;                   // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;         // which half of the columns this warp owns
+        const int cbeg = (p.BN >= 64) ? half * (p.BN >> 1) : 0;
+        const int cend = (p.BN >= 64) ? cbeg + (p.BN >> 1) : (half == 0 ? p.BN : 0);
         const int r = q * 32 + lane;              // accumulator row == pixel within the tile
         const int tx = r & (p.TW - 1), ty = r >> p.TWlog2;
         const bool leaky = p.act == ACT_LEAKY, leaky2 = p.act2 == ACT_LEAKY;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-            const int n_idx = t % p.nt;
-            const int m = t / p.nt;
+        long long w_tfull = 0; const long long t_begin = clock64();
+        for (int w = w_first; w < p.num_work; w += w_step) {
+            const int n_idx = w % p.nt;
+            const int m = (CG == 2) ? 2 * (w / p.nt) + (int)rank : w / p.nt;
             const int ox = (m % p.xt) * p.TW + tx;
             const int J = (m / p.xt) * p.TH + ty;
             const int n0 = n_idx * p.BN;
             const int img = J / p.PR;
             const int oy = J - img * p.PR - p.row_off;
-            const bool valid = (img < p.N) && (oy >= 0) && (oy < p.OH) && (ox < p.OW);
+            const bool valid = (img < p.N) && (oy >= 0) && (oy < p.OH) && (ox < p.OW) && !(p.dbg & 4);
             const long pix = ((long)(img * p.OHp + oy + 1) * p.OWp + ox + 1);
             char *orow = p.out + pix * p.out_ldc * (p.out_bf16 ? 2 : 4);
             const char *rrow = (p.res && valid) ? p.res + pix * p.res_ldc * 2 : nullptr;
@@ -274,10 +378,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         dst[g] = __ldg(reinterpret_cast<const uint4 *>(rrow + (size_t)(n0 + f0) * 2) + g);
                 }
             };
-            load_res(0, rv[0]);
-            if (p.BN > 32) load_res(32, rv[1]);
+            const bool coalesced = p.out_bf16 && (cend - cbeg) >= 64 && !p.no_coalesce;
+            if (!coalesced) {
+                if (cbeg < cend) load_res(cbeg, rv[0]);
+                if (cend - cbeg > 32) load_res(cbeg + 32, rv[1]);
+            }
 
-            mbar_wait(tfull_bar(acc), acc_phase, 3);
+            { const long long c0 = clock64(); mbar_wait(tfull_bar(acc), acc_phase, 3); w_tfull += clock64() - c0; }
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
 
@@ -287,21 +394,21 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     float a = __uint_as_float(v[j]) + bs[f0 + j];
-                    x[j] = leaky ? ((a > 0.f) ? a : 0.1f * a) : a;
+                    x[j] = leaky ? fmaxf(a, 0.1f * a) : a;   // == a > 0 ? a : 0.1a
                 }
                 if (p.res) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        const uint32_t w[4] = {rr[g].x, rr[g].y, rr[g].z, rr[g].w};
+                        const uint32_t wv[4] = {rr[g].x, rr[g].y, rr[g].z, rr[g].w};
 #pragma unroll
                         for (int h = 0; h < 4; ++h) {
-                            x[g * 8 + 2 * h] += __uint_as_float(w[h] << 16);
-                            x[g * 8 + 2 * h + 1] += __uint_as_float(w[h] & 0xffff0000u);
+                            x[g * 8 + 2 * h] += __uint_as_float(wv[h] << 16);
+                            x[g * 8 + 2 * h + 1] += __uint_as_float(wv[h] & 0xffff0000u);
                         }
                     }
                     if (leaky2) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) x[j] = (x[j] > 0.f) ? x[j] : 0.1f * x[j];
+                        for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.1f * x[j]);
                     }
                 }
                 if (p.out_bf16) {
@@ -326,13 +433,83 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 }
             };
 
-            if (p.BN == 32) {
-                uint32_t v0[32];
-                tmem_ld32(taddr, v0);
-                tmem_ld_wait();
-                finish(v0, rv[0], 0);
-            } else {
-                for (int f0 = 0; f0 < p.BN; f0 += 64) {
+            if (p.out_bf16 && (cend - cbeg) >= 64 && !p.no_coalesce) {
+                // ---- coalesced path: every global access of this warp is a run of whole 128-byte lines.
+                // Each warp owns 32 accumulator rows; per 64-column slab a row is 128 B of bf16.  Rows are
+                // transposed through the warp's private swizzled staging tile so that one warp instruction moves
+                // 4 rows x 128 B instead of 32 rows x 16 B (the latter costs 32 LSU cycles per instruction and made
+                // the epilogue the bottleneck of every layer, profiles/r01_notes.md).
+                const uint32_t stg = stg_base + (uint32_t)(warp - 2) * 4096u;
+                const int srow = lane >> 3, schunk = lane & 7;
+                const unsigned long long obase = (unsigned long long)(uintptr_t)orow;
+                const unsigned long long rbase = (unsigned long long)(uintptr_t)rrow;
+                const int vflag = valid ? 1 : 0;
+                auto stage_addr = [&](int row, int chunk) { return stg + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4); };
+                auto res_to_stage = [&](int f0) {     // coalesced global -> staging
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = i * 4 + srow;
+                        const unsigned long long rp = __shfl_sync(0xffffffffu, rbase, row);
+                        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                        if (rp && (n0 + f0 + schunk * 8) < p.n_store)
+                            v = __ldg(reinterpret_cast<const uint4 *>(rp + (size_t)(n0 + f0) * 2) + schunk);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(row, schunk)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                    }
+                };
+                if (p.res) res_to_stage(cbeg);
+                for (int f0 = cbeg; f0 < cend; f0 += 64) {
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(taddr + (uint32_t)f0, v0);
+                    tmem_ld32(taddr + (uint32_t)f0 + 32u, v1);
+                    tmem_ld_wait();
+                    float x[64];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float a0 = __uint_as_float(v0[j]) + bs[f0 + j], a1 = __uint_as_float(v1[j]) + bs[f0 + 32 + j];
+                        x[j] = leaky ? fmaxf(a0, 0.1f * a0) : a0;
+                        x[32 + j] = leaky ? fmaxf(a1, 0.1f * a1) : a1;
+                    }
+                    if (p.res) {
+                        __syncwarp();
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {          // own row back from staging
+                            uint32_t w0, w1, w2, w3;
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(stage_addr(lane, c)) : "memory");
+                            const uint32_t wv[4] = {w0, w1, w2, w3};
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) {
+                                x[c * 8 + 2 * h] += __uint_as_float(wv[h] << 16);
+                                x[c * 8 + 2 * h + 1] += __uint_as_float(wv[h] & 0xffff0000u);
+                            }
+                        }
+                        if (leaky2) {
+#pragma unroll
+                            for (int j = 0; j < 64; ++j) x[j] = fmaxf(x[j], 0.1f * x[j]);
+                        }
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)                 // own row -> staging
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(lane, c)),
+                                     "r"(pack_bf16x2(x[c * 8 + 0], x[c * 8 + 1])), "r"(pack_bf16x2(x[c * 8 + 2], x[c * 8 + 3])),
+                                     "r"(pack_bf16x2(x[c * 8 + 4], x[c * 8 + 5])), "r"(pack_bf16x2(x[c * 8 + 6], x[c * 8 + 7])) : "memory");
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {               // staging -> coalesced global
+                        const int row = i * 4 + srow;
+                        const unsigned long long op = __shfl_sync(0xffffffffu, obase, row);
+                        const int ok = __shfl_sync(0xffffffffu, vflag, row);
+                        uint32_t w0, w1, w2, w3;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(stage_addr(row, schunk)) : "memory");
+                        if (ok && (n0 + f0 + schunk * 8) < p.n_store)
+                            *(reinterpret_cast<uint4 *>(op + (size_t)(n0 + f0) * 2) + schunk) = make_uint4(w0, w1, w2, w3);
+                    }
+                    __syncwarp();
+                    if (p.res && f0 + 64 < cend) res_to_stage(f0 + 64);   // next slab's residual in flight
+                }
+            } else
+            for (int f0 = cbeg; f0 < cend; f0 += 64) {
+                if (cend - f0 >= 64) {
                     uint32_t v0[32], v1[32];
                     tmem_ld32(taddr + (uint32_t)f0, v0);
                     tmem_ld32(taddr + (uint32_t)f0 + 32u, v1);
@@ -340,22 +517,36 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     uint4 r0[4], r1[4];
 #pragma unroll
                     for (int g = 0; g < 4; ++g) { r0[g] = rv[0][g]; r1[g] = rv[1][g]; }
-                    if (f0 + 64 < p.BN) { load_res(f0 + 64, rv[0]); load_res(f0 + 96, rv[1]); }   // next slab in flight
+                    if (f0 + 64 < cend) {                                   // next slab's residual in flight
+                        load_res(f0 + 64, rv[0]);
+                        if (cend - (f0 + 64) > 32) load_res(f0 + 96, rv[1]);
+                    }
                     finish(v0, r0, f0);
                     finish(v1, r1, f0 + 32);
+                } else {
+                    uint32_t v0[32];
+                    tmem_ld32(taddr + (uint32_t)f0, v0);
+                    tmem_ld_wait();
+                    finish(v0, rv[0], f0);
                 }
             }
             tc_fence_before();
-            mbar_arrive(tempty_bar(acc));   // 128 arrivals hand the accumulator back to the MMA warp
+            // all epilogue threads (of both CTAs) hand the accumulator back to the (leader's) MMA warp
+            __syncwarp();
+            if (lane == 0) { if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_remote(tempty_bar(acc), 0); }
             if (++acc == TC_ACC) { acc = 0; acc_phase ^= 1u; }
         }
+        if (p.stats && warp == 2 && lane == 0) { p.stats[blockIdx.x * 8 + 5] = (unsigned long long)w_tfull; p.stats[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - t_begin); }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+        if constexpr (CG == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     }
 }
 
@@ -383,6 +574,7 @@ struct TcPlan {
     TcParams p;
     int grid;
     size_t smem;
+    char desc[96];
 };
 
 int pick_bk(int C) { return (C % 64 == 0) ? 64 : (C % 32 == 0) ? 32 : (C % 16 == 0) ? 16 : 0; }
@@ -433,18 +625,22 @@ void *tc_make_plan(const Layer &l, const TV &in, const TV &out, bool out_bf16, c
     p.jt = (int)((rows + p.TH - 1) / p.TH);
     p.nt = (l.n + BN - 1) / BN;
     p.num_tiles = p.xt * p.jt * p.nt;
+    // CTA pairs (cta_group::2) for the wide tiles: halves the B bytes each SM has to pull through its TMA unit
+    const char *cg_env = getenv("YB_TC_CG");
+    p.cg = (BN == 256 && p.xt * p.jt >= 2 && !(cg_env && atoi(cg_env) == 1)) ? 2 : 1;
+    p.num_work = (p.cg == 2) ? ((p.xt * p.jt + 1) / 2) * p.nt : p.num_tiles;
     p.a_bytes = (uint32_t)(TC_BM * BK * 2);
-    p.b_bytes = (uint32_t)(BN * BK * 2);
-    p.nt = (l.n + BN - 1) / BN;
+    p.b_bytes = (uint32_t)((BN / p.cg) * BK * 2);   // per CTA
     // several K-blocks per stage when they are small: the single MMA-issuing thread pays a fixed barrier round
     // trip per stage, which dominated the C<=64 layers (profiles/r01_notes.md)
     p.sps = (int)std::max<uint32_t>(1, std::min<uint32_t>(4, (64u * 1024u) / (p.a_bytes + p.b_bytes)));
+    if (getenv("YB_TC_SPS")) p.sps = std::max(1, atoi(getenv("YB_TC_SPS")));
     p.sps = std::min(p.sps, p.kblocks);
     p.stage_bytes = (uint32_t)p.sps * (p.a_bytes + p.b_bytes);
-    p.stages = (int)std::min<size_t>(8, (200 * 1024 - sizeof(float) * (size_t)p.nt * BN) / p.stage_bytes);
+    p.stages = (int)std::min<size_t>(8, (192 * 1024 - sizeof(float) * (size_t)p.nt * BN) / p.stage_bytes);
     if (p.stages < 2) fatal_throw("tc plan: tile does not fit shared memory");
     // UMMA instruction descriptor (kind::f16): D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
-    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TC_BM * p.cg) >> 4) << 24);
     // smem descriptor high word: SBO (8 rows * row bytes) >> 4 at bits 32..45, version 1 at bit 46, swizzle at 61..63
     const uint32_t row_bytes = (uint32_t)BK * 2;
     const uint32_t layout = row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;
@@ -458,6 +654,9 @@ void *tc_make_plan(const Layer &l, const TV &in, const TV &out, bool out_bf16, c
     if (res.base && !res_bf16) fatal_throw("tc plan: residual must be bf16");
     if (res.base && res_bf16 && (res.ldc % 8 != 0 || (reinterpret_cast<uintptr_t>(res.base) & 15))) fatal_throw("tc plan: residual alignment");
     p.bias = d_bias; p.act = l.activation; p.act2 = act2;
+    p.dbg = getenv("YB_TC_DBG") ? atoi(getenv("YB_TC_DBG")) : 0;
+    p.no_coalesce = getenv("YB_TC_NO_COALESCE") ? 1 : 0;
+    snprintf(plan->desc, sizeof(plan->desc), "%dx%dx%d -> n%d k%d s%d", l.c, l.h, l.w, l.n, l.size, l.stride);
     uint32_t cols = 32; while (cols < (uint32_t)(TC_ACC * BN)) cols *= 2;
     p.tmem_cols = cols;
 
@@ -488,7 +687,7 @@ void *tc_make_plan(const Layer &l, const TV &in, const TV &out, bool out_bf16, c
         const cuuint64_t K = (cuuint64_t)l.size * l.size * l.c;
         cuuint64_t dims[2] = {K, (cuuint64_t)ldn};
         cuuint64_t strides[1] = {K * 2};
-        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)(BN / p.cg)};   // CG=2: each CTA of the pair loads half of the filters
         cuuint32_t es[2] = {1, 1};
         r = enc(&plan->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(d_weights_bf16), dims, strides, box, es,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -497,19 +696,49 @@ void *tc_make_plan(const Layer &l, const TV &in, const TV &out, bool out_bf16, c
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    plan->grid = std::min(p.num_tiles, sms);
+    plan->grid = (p.cg == 2) ? 2 * std::min(p.num_work, sms / 2) : std::min(p.num_tiles, sms);
+    if (getenv("YB_TC_STATS")) {
+        cudaMalloc(&p.stats, sizeof(unsigned long long) * 8 * plan->grid);
+        cudaMemset(p.stats, 0, sizeof(unsigned long long) * 8 * plan->grid);
+    }
     plan->smem = (size_t)p.stages * p.stage_bytes + 1024 /*alignment slack*/ + 8 * (2 * p.stages + 2 * TC_ACC) + 16 +
-                 sizeof(float) * (size_t)p.nt * BN /*bias*/;
-    if (cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+                 sizeof(float) * (size_t)p.nt * BN /*bias*/ + 128 + 4096 * TC_EPI_WARPS /*epilogue staging*/;
+    if (cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_conv_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
         fatal_throw("cudaFuncSetAttribute(k_conv_tc) failed");
     return plan;
 }
 
 void tc_launch(void *vp, cudaStream_t s) {
     TcPlan *plan = reinterpret_cast<TcPlan *>(vp);
-    k_conv_tc<<<plan->grid, TC_THREADS, plan->smem, s>>>(plan->tmA, plan->tmB, plan->p);
+    if (plan->p.cg == 2) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)plan->grid); cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = plan->smem; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, k_conv_tc<2>, plan->tmA, plan->tmB, plan->p);
+    } else {
+        k_conv_tc<1><<<plan->grid, TC_THREADS, plan->smem, s>>>(plan->tmA, plan->tmB, plan->p);
+    }
 }
 
-void tc_free_plan(void *vp) { delete reinterpret_cast<TcPlan *>(vp); }
+void tc_free_plan(void *vp) {
+    TcPlan *plan = reinterpret_cast<TcPlan *>(vp);
+    if (plan && plan->p.stats) {   // diagnostic dump: mean cycles per CTA of the LAST launch
+        std::vector<unsigned long long> h(8 * (size_t)plan->grid);
+        cudaDeviceSynchronize();
+        cudaMemcpy(h.data(), plan->p.stats, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+        double m[8] = {0};
+        for (int b = 0; b < plan->grid; ++b) for (int k = 0; k < 8; ++k) m[k] += (double)h[8 * b + k] / plan->grid;
+        fprintf(stderr, "TCSTATS %-28s cg %d tiles/cta %.1f kb %d sps %d BN %d | producer: wait_empty %.0f tma_issue %.0f total %.0f | mma: wait_full %.0f "
+                        "wait_tempty %.0f total %.0f | epi: wait_tfull %.0f total %.0f\n", plan->desc, plan->p.cg,
+                (double)plan->p.num_tiles / plan->grid * 1.0, plan->p.kblocks, plan->p.sps, plan->p.BN, m[0], m[7], m[1], m[2], m[3], m[4], m[5], m[6]);
+        cudaFree(plan->p.stats);
+    }
+    delete plan;
+}
 
 }  // namespace yb
