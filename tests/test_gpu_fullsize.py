@@ -64,6 +64,8 @@ def test_yolov3_tiny_416_fp32_and_int8_vs_reference(workdir):
             assert util.rel_l2(o[b], exp[b][i].reshape(o[b].shape)) <= 1e-3, (i, b)
     netq = yb.load_network(cfg, wts, batch=2, quantized=1)
     netq.predict(x, quantized=True)
+    kinds = [k for _, k, _ in netq.profile(quantized=True)]
+    assert kinds.count("conv_tc_i8") >= 8, kinds   # the s8 x s8 -> s32 tcgen05 path carries the INT8 layers
     expq = _ref_outputs(cfg, wts, x, 1, "scalar")
     for i, o in netq.detection_outputs().items():
         for b in range(2):

@@ -46,6 +46,10 @@ struct TcParams {
     int num_tiles;
     int num_work;             // work items of the persistent loop: num_tiles (CG=1) or pairs of m-tiles x nt (CG=2)
     int cg;                   // 1, or 2 = CTA pairs (cta_group::2)
+    int kind;                 // 0: bf16 x bf16 -> f32 (kind::f16);  1: s8 x s8 -> s32 (kind::i8), exact requantising epilogue
+    int kk;                   // MMAs per K-block (BK bytes / 32)
+    float alpha1;             // INT8: R_MULT / (input_mult * weights_mult)
+    int *acc_out;             // INT8: optional raw s32 accumulators, NCHW (tests)
     int PR, row_off;          // merged-row pitch per image; output row = (J % PR) - row_off
     int OH, OW, OHp, OWp;
     int size, cblocks, kblocks;
@@ -128,6 +132,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -303,7 +313,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (leader && elect_one()) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            const int kk = p.BK / 16, sps = p.sps, kblocks = p.kblocks, stages = p.stages, BN = p.BN;
+            const int kk = p.kk, kind = p.kind, sps = p.sps, kblocks = p.kblocks, stages = p.stages, BN = p.BN;
             const uint32_t a_bytes = p.a_bytes, b_bytes = p.b_bytes, stage_bytes = p.stage_bytes, idesc = p.idesc, dbg = (uint32_t)p.dbg;
             const uint32_t b_off = (uint32_t)sps * a_bytes;
             const uint64_t hi = (uint64_t)p.desc_hi << 32;
@@ -325,6 +335,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         uint64_t bdesc = hi | (uint64_t)((((b_base + (uint32_t)j * b_bytes) & 0x3FFFFu) >> 4) | (1u << 16));
                         for (int k = 0; k < kk; ++k) {
                             if constexpr (CG == 2) umma2_bf16(d_tmem, adesc, bdesc, idesc, (uint32_t)((kb0 | j | k) != 0));
+                            else if (kind == 1) umma_i8(d_tmem, adesc, bdesc, idesc, (uint32_t)((kb0 | j | k) != 0));
                             else umma_bf16(d_tmem, adesc, bdesc, idesc, (uint32_t)((kb0 | j | k) != 0));
                             adesc += 2; bdesc += 2;
                         }
@@ -378,7 +389,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         dst[g] = __ldg(reinterpret_cast<const uint4 *>(rrow + (size_t)(n0 + f0) * 2) + g);
                 }
             };
-            const bool coalesced = p.out_bf16 && (cend - cbeg) >= 64 && !p.no_coalesce;
+            const bool coalesced = (p.out_bf16 && (cend - cbeg) >= 64 && !p.no_coalesce) || p.kind == 1;
             if (!coalesced) {
                 if (cbeg < cend) load_res(cbeg, rv[0]);
                 if (cend - cbeg > 32) load_res(cbeg + 32, rv[1]);
@@ -433,6 +444,39 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 }
             };
 
+            if (p.kind == 1) {
+                // ---- INT8: exact requantisation of the reference (yolov2_forward_network_quantized.c:474-490, :598-627):
+                // q16 = clamp(+-32767, acc / 32) [C truncating division]; y = (float)q16 * ALPHA1; y += bias; leaky: y / 10.
+                float *orow_f = reinterpret_cast<float *>(orow);
+                for (int f0 = cbeg; f0 < cend; f0 += 32) {
+                    uint32_t v0[32];
+                    tmem_ld32(taddr + (uint32_t)f0, v0);
+                    tmem_ld_wait();
+                    if (!valid) continue;
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        if (n0 + f0 + g * 4 >= p.n_store) break;
+                        float y[4];
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            const int a = (int)v0[g * 4 + h];
+                            int q16 = a / 32;
+                            q16 = q16 > 32767 ? 32767 : (q16 < -32767 ? -32767 : q16);
+                            float t = __fmul_rn((float)q16, p.alpha1);
+                            t = __fadd_rn(t, bs[f0 + g * 4 + h]);
+                            y[h] = (p.act == ACT_LEAKY) ? ((t > 0.f) ? t : __fdiv_rn(t, 10.f)) : t;
+                        }
+                        *reinterpret_cast<float4 *>(orow_f + n0 + f0 + g * 4) = make_float4(y[0], y[1], y[2], y[3]);
+                    }
+                    if (p.acc_out) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int f = n0 + f0 + j;
+                            if (f < p.n) p.acc_out[(((size_t)img * p.n + f) * p.OH + oy) * p.OW + ox] = (int)v0[j];
+                        }
+                    }
+                }
+            } else
             if (p.out_bf16 && (cend - cbeg) >= 64 && !p.no_coalesce) {
                 // ---- coalesced path: every global access of this warp is a run of whole 128-byte lines.
                 // Each warp owns 32 accumulator rows; per 64-column slab a row is 128 B of bf16.  Rows are
@@ -578,6 +622,7 @@ struct TcPlan {
 };
 
 int pick_bk(int C) { return (C % 64 == 0) ? 64 : (C % 32 == 0) ? 32 : (C % 16 == 0) ? 16 : 0; }
+int pick_bk_i8(int cpad) { return (cpad % 128 == 0) ? 128 : (cpad % 64 == 0) ? 64 : (cpad % 32 == 0) ? 32 : 0; }
 int pick_bn(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : 256; }
 
 }  // namespace
@@ -596,17 +641,22 @@ int tc_conv_supported(const Layer &l, const TV &in, const TV &out, bool out_bf16
     return 1;
 }
 
-void *tc_make_plan(const Layer &l, const TV &in, const TV &out, bool out_bf16, const TV &res, bool res_bf16,
-                   int act2, const void *d_weights_bf16, int ldn, const float *d_bias) {
+static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &out, bool out_bf16, const TV &res,
+                              bool res_bf16, int act2, const void *d_weights_bf16, int ldn, const float *d_bias,
+                              float alpha1, int *acc_out) {
     TcPlan *plan = new TcPlan();
     memset(plan, 0, sizeof(*plan));
     TcParams &p = plan->p;
-    const int BK = pick_bk(l.c), BN = pick_bn(l.n);
+    const int esz = kind == 1 ? 1 : 2;                       // operand element size
+    const int cin = kind == 1 ? in.ldc : l.c;                // INT8: channels padded with zeros in both operands
+    const int BK = kind == 1 ? pick_bk_i8(cin) : pick_bk(l.c), BN = pick_bn(l.n);
+    p.kind = kind; p.alpha1 = alpha1; p.acc_out = acc_out;
+    p.kk = BK * esz / 32;
     const bool s2 = l.stride == 2;
     p.N = in.N;
     p.OH = l.out_h; p.OW = l.out_w; p.OHp = out.Hp; p.OWp = out.Wp;
     p.size = l.size; p.BK = BK; p.BN = BN;
-    p.cblocks = l.c / BK; p.kblocks = l.size * l.size * p.cblocks;
+    p.cblocks = cin / BK; p.kblocks = l.size * l.size * p.cblocks;
     p.stride2 = s2 ? 1 : 0;
     p.xoff = 1 - l.pad; p.yoff = -l.pad;
     p.PR = s2 ? (in.Hp / 2) : in.Hp;
@@ -627,10 +677,10 @@ void *tc_make_plan(const Layer &l, const TV &in, const TV &out, bool out_bf16, c
     p.num_tiles = p.xt * p.jt * p.nt;
     // CTA pairs (cta_group::2) for the wide tiles: halves the B bytes each SM has to pull through its TMA unit
     const char *cg_env = getenv("YB_TC_CG");
-    p.cg = (BN == 256 && p.xt * p.jt >= 2 && !(cg_env && atoi(cg_env) == 1)) ? 2 : 1;
+    p.cg = (kind == 0 && BN == 256 && p.xt * p.jt >= 2 && !(cg_env && atoi(cg_env) == 1)) ? 2 : 1;
     p.num_work = (p.cg == 2) ? ((p.xt * p.jt + 1) / 2) * p.nt : p.num_tiles;
-    p.a_bytes = (uint32_t)(TC_BM * BK * 2);
-    p.b_bytes = (uint32_t)((BN / p.cg) * BK * 2);   // per CTA
+    p.a_bytes = (uint32_t)(TC_BM * BK * esz);
+    p.b_bytes = (uint32_t)((BN / p.cg) * BK * esz);   // per CTA
     // several K-blocks per stage when they are small: the single MMA-issuing thread pays a fixed barrier round
     // trip per stage, which dominated the C<=64 layers (profiles/r01_notes.md)
     p.sps = (int)std::max<uint32_t>(1, std::min<uint32_t>(4, (64u * 1024u) / (p.a_bytes + p.b_bytes)));
@@ -641,8 +691,10 @@ void *tc_make_plan(const Layer &l, const TV &in, const TV &out, bool out_bf16, c
     if (p.stages < 2) fatal_throw("tc plan: tile does not fit shared memory");
     // UMMA instruction descriptor (kind::f16): D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TC_BM * p.cg) >> 4) << 24);
+    // kind::i8: D = s32 (2 at bit 4), A = B = signed 8 bit (1 at bits 7 / 10)
+    if (kind == 1) p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     // smem descriptor high word: SBO (8 rows * row bytes) >> 4 at bits 32..45, version 1 at bit 46, swizzle at 61..63
-    const uint32_t row_bytes = (uint32_t)BK * 2;
+    const uint32_t row_bytes = (uint32_t)(BK * esz);
     const uint32_t layout = row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;
     p.desc_hi = ((8u * row_bytes) >> 4) | (1u << 14) | (layout << 29);
     p.out = out.base; p.out_ldc = out.ldc; p.out_bf16 = out_bf16 ? 1 : 0;
@@ -663,33 +715,34 @@ void *tc_make_plan(const Layer &l, const TV &in, const TV &out, bool out_bf16, c
     const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                  : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
     EncodeTiledFn enc = encode_fn();
+    const CUtensorMapDataType dtype = kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     CUresult r;
     if (!s2) {
         // activation view (c, x_padded, merged padded rows)
-        cuuint64_t dims[3] = {(cuuint64_t)l.c, (cuuint64_t)in.Wp, (cuuint64_t)in.N * in.Hp};
-        cuuint64_t strides[2] = {(cuuint64_t)in.ldc * 2, (cuuint64_t)in.Wp * in.ldc * 2};
+        cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)in.Wp, (cuuint64_t)in.N * in.Hp};
+        cuuint64_t strides[2] = {(cuuint64_t)in.ldc * esz, (cuuint64_t)in.Wp * in.ldc * esz};
         cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)p.TW, (cuuint32_t)p.TH};
         cuuint32_t es[3] = {1, 1, 1};
-        r = enc(&plan->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, in.base, dims, strides, box, es,
+        r = enc(&plan->tmA, dtype, 3, in.base, dims, strides, box, es,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
         // stride 2: (c, x parity, x half, y parity, merged y half)
-        cuuint64_t dims[5] = {(cuuint64_t)l.c, 2, (cuuint64_t)in.Wp / 2, 2, (cuuint64_t)in.N * in.Hp / 2};
-        cuuint64_t strides[4] = {(cuuint64_t)in.ldc * 2, (cuuint64_t)in.ldc * 4, (cuuint64_t)in.Wp * in.ldc * 2,
-                                 (cuuint64_t)in.Wp * in.ldc * 4};
+        cuuint64_t dims[5] = {(cuuint64_t)cin, 2, (cuuint64_t)in.Wp / 2, 2, (cuuint64_t)in.N * in.Hp / 2};
+        cuuint64_t strides[4] = {(cuuint64_t)in.ldc * esz, (cuuint64_t)in.ldc * 2 * esz, (cuuint64_t)in.Wp * in.ldc * esz,
+                                 (cuuint64_t)in.Wp * in.ldc * 2 * esz};
         cuuint32_t box[5] = {(cuuint32_t)BK, 1, (cuuint32_t)p.TW, 1, (cuuint32_t)p.TH};
         cuuint32_t es[5] = {1, 1, 1, 1, 1};
-        r = enc(&plan->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, in.base, dims, strides, box, es,
+        r = enc(&plan->tmA, dtype, 5, in.base, dims, strides, box, es,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
     if (r != CUDA_SUCCESS) { delete plan; fatal_throw("cuTensorMapEncodeTiled(A) failed: " + std::to_string((int)r)); }
     {
-        const cuuint64_t K = (cuuint64_t)l.size * l.size * l.c;
+        const cuuint64_t K = (cuuint64_t)l.size * l.size * cin;
         cuuint64_t dims[2] = {K, (cuuint64_t)ldn};
-        cuuint64_t strides[1] = {K * 2};
+        cuuint64_t strides[1] = {K * esz};
         cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)(BN / p.cg)};   // CG=2: each CTA of the pair loads half of the filters
         cuuint32_t es[2] = {1, 1};
-        r = enc(&plan->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(d_weights_bf16), dims, strides, box, es,
+        r = enc(&plan->tmB, dtype, 2, const_cast<void *>(d_weights_bf16), dims, strides, box, es,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { delete plan; fatal_throw("cuTensorMapEncodeTiled(B) failed: " + std::to_string((int)r)); }
     }
@@ -707,6 +760,30 @@ void *tc_make_plan(const Layer &l, const TV &in, const TV &out, bool out_bf16, c
         cudaFuncSetAttribute(k_conv_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
         fatal_throw("cudaFuncSetAttribute(k_conv_tc) failed");
     return plan;
+}
+
+void *tc_make_plan(const Layer &l, const TV &in, const TV &out, bool out_bf16, const TV &res, bool res_bf16,
+                   int act2, const void *d_weights_bf16, int ldn, const float *d_bias) {
+    return make_plan_common(0, l, in, out, out_bf16, res, res_bf16, act2, d_weights_bf16, ldn, d_bias, 0.f, nullptr);
+}
+
+// INT8 variant (reference forward_convolutional_layer_q, yolov2_forward_network_quantized.c:527-631) on
+// tcgen05.mma kind::i8: `q` is the quantised s8 activation (padded NHWC, channels zero-padded to q.ldc), weights are
+// s8 [ldn][taps][q.ldc]; output f32.
+int tc_i8_supported(const Layer &l, const TV &q, const TV &out) {
+    if (pick_bk_i8(q.ldc) == 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(q.base) & 15) != 0 || q.P != 1 || q.ldc % 16 != 0) return 0;
+    const bool s1 = l.stride == 1 && ((l.size == 3 && l.pad == 1) || (l.size == 1 && l.pad == 0));
+    const bool s2 = l.stride == 2 && l.size == 3 && l.pad == 1 && (l.h % 2 == 0) && (l.w % 2 == 0);
+    if (!s1 && !s2) return 0;
+    if (!out.base || (reinterpret_cast<uintptr_t>(out.base) & 15) != 0 || out.ldc % 4 != 0 || l.n < 8) return 0;
+    if (l.activation != YB_LEAKY && l.activation != YB_LINEAR) return 0;
+    return 1;
+}
+void *tc_make_plan_i8(const Layer &l, const TV &q, const TV &out, const void *d_weights_s8, int ldn, const float *d_bias,
+                      float alpha1, int *acc_out) {
+    TV none{};
+    return make_plan_common(1, l, q, out, false, none, false, ACT_LINEAR, d_weights_s8, ldn, d_bias, alpha1, acc_out);
 }
 
 void tc_launch(void *vp, cudaStream_t s) {

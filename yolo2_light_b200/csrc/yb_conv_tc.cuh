@@ -13,6 +13,10 @@ int tc_conv_supported(const Layer &l, const TV &in, const TV &out, bool out_bf16
 // builds the per-layer launch state (TMA tensor maps, tile schedule); throws yb::Error on failure
 void *tc_make_plan(const Layer &l, const TV &in, const TV &out, bool out_bf16, const TV &res, bool res_bf16,
                    int act2, const void *d_weights_bf16, int ldn, const float *d_bias);
+// INT8 (kind::i8) variant
+int tc_i8_supported(const Layer &l, const TV &q, const TV &out);
+void *tc_make_plan_i8(const Layer &l, const TV &q, const TV &out, const void *d_weights_s8, int ldn, const float *d_bias,
+                      float alpha1, int *acc_out);
 void tc_launch(void *plan, cudaStream_t s);
 void tc_free_plan(void *plan);
 

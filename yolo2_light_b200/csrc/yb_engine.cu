@@ -280,7 +280,7 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
             side_off[i] = act_total;
             act_total += align_up(tv_bytes(B, l.h, l.w, side_ld[i], P, DT_BITS), 1024);
         } else if (v == 2) {
-            side_ld[i] = (int)align_up(l.c, 16);
+            side_ld[i] = (int)align_up(l.c, 32);   // zero-padded channels: every INT8 layer fits the kind::i8 tensor-core tile
             side_off[i] = act_total;
             act_total += align_up(tv_bytes(B, l.h, l.w, side_ld[i], P, DT_S8), 1024);
         }
@@ -554,18 +554,28 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                     const int g = grid_for(total);
                     e->ops.push_back(Op{OP_QUANTIZE, i, [tin, q, mult, g](cudaStream_t s) { k_quantize<float><<<g, 256, 0, s>>>(tin, q, mult); }});
                 }
+                int *acc_dbg = nullptr;
+                if (opt.keep_counts) {
+                    e->counts_count[i] = (size_t)B * l.n * l.out_h * l.out_w;
+                    CUDA_OK(cudaMalloc(&e->d_counts[i], e->counts_count[i] * sizeof(int32_t)));
+                    acc_dbg = e->d_counts[i];
+                }
+                const float alpha1 = 32 / (l.input_quant_multipler * l.weights_quant_multipler);   // ALPHA1, ..._quantized.c:598
+                if (!getenv("YB_NO_TC") && tc_i8_supported(l, q, tout)) {
+                    // s8 x s8 -> s32 on tcgen05 (kind::i8); weights [ldn][taps][cpad] are already K-major
+                    void *plan = tc_make_plan_i8(l, q, tout, e->w_arena + cw[i].w_s8, cw[i].ldn,
+                                                 reinterpret_cast<const float *>(e->w_arena + cw[i].bias), alpha1, acc_dbg);
+                    e->tc_plans.push_back(plan);
+                    e->ops.push_back(Op{OP_CONV_TC_I8, i, [plan](cudaStream_t s) { tc_launch(plan, s); }});
+                    break;
+                }
                 Int8P p{};
                 p.q = q; p.out = tout;
                 p.w = reinterpret_cast<const uint32_t *>(e->w_arena + cw[i].w_s8);
                 p.bias = reinterpret_cast<const float *>(e->w_arena + cw[i].bias);
-                p.alpha1 = 32 / (l.input_quant_multipler * l.weights_quant_multipler);   // ALPHA1, ..._quantized.c:598
+                p.alpha1 = alpha1;
                 p.n = l.n; p.size = l.size; p.stride = l.stride; p.pad = l.pad; p.act = l.activation;
-                p.CW = cpad / 4; p.M = M; p.acc_out = nullptr;
-                if (opt.keep_counts) {
-                    e->counts_count[i] = (size_t)B * l.n * l.out_h * l.out_w;
-                    CUDA_OK(cudaMalloc(&e->d_counts[i], e->counts_count[i] * sizeof(int32_t)));
-                    p.acc_out = e->d_counts[i];
-                }
+                p.CW = cpad / 4; p.M = M; p.acc_out = acc_dbg;
                 dim3 grid((unsigned)((M + 63) / 64), (unsigned)((l.n + 63) / 64));
                 e->ops.push_back(Op{OP_CONV_INT8, i, [p, grid](cudaStream_t s) { k_conv_int8_simt<<<grid, 256, 0, s>>>(p); }});
             }
@@ -577,8 +587,14 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
             const int size = l.size, stride = l.stride, pad = l.pad;
             const int g = grid_for((long)B * l.out_h * l.out_w * l.out_c);
             const int dt = in_dt;
-            e->ops.push_back(Op{OP_MAXPOOL, i, [tin, tout, size, stride, pad, g, dt](cudaStream_t s) {
-                if (dt == DT_F32) k_maxpool<float><<<g, 256, 0, s>>>(tin, tout, size, stride, pad);
+            const int esz = (int)dt_size(dt);
+            const bool vec = (l.out_c * esz) % 16 == 0 && (tin.ldc * esz) % 16 == 0 && (tout.ldc * esz) % 16 == 0 &&
+                             (reinterpret_cast<uintptr_t>(tin.base) & 15) == 0 && (reinterpret_cast<uintptr_t>(tout.base) & 15) == 0;
+            const int gv = grid_for((long)B * l.out_h * l.out_w * ((l.out_c * esz) / 16 + 1));
+            e->ops.push_back(Op{OP_MAXPOOL, i, [tin, tout, size, stride, pad, g, dt, vec, gv](cudaStream_t s) {
+                if (vec && dt == DT_F32) k_maxpool_vec<float><<<gv, 256, 0, s>>>(tin, tout, size, stride, pad);
+                else if (vec) k_maxpool_vec<__nv_bfloat16><<<gv, 256, 0, s>>>(tin, tout, size, stride, pad);
+                else if (dt == DT_F32) k_maxpool<float><<<g, 256, 0, s>>>(tin, tout, size, stride, pad);
                 else k_maxpool<__nv_bfloat16><<<g, 256, 0, s>>>(tin, tout, size, stride, pad);
             }});
             break;

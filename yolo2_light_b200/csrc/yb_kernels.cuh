@@ -548,6 +548,42 @@ __global__ void k_maxpool(TV in, TV out, int size, int stride, int pad) {
     }
 }
 
+// same, 16 bytes (4 f32 / 8 bf16 channels) per thread
+template <typename T>
+__global__ void k_maxpool_vec(TV in, TV out, int size, int stride, int pad) {
+    constexpr int V = 16 / sizeof(T);
+    const int chunks = out.C / V;
+    const long total = (long)out.N * out.H * out.W * chunks;
+    const int off = -pad / 2;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % chunks);
+        const long pxl = i / chunks;
+        const int x = (int)(pxl % out.W);
+        const int y = (int)((pxl / out.W) % out.H);
+        const int n = (int)(pxl / ((long)out.W * out.H));
+        float m[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) m[k] = -3.402823466e+38f;
+        for (int a = 0; a < size; ++a) {
+            const int iy = off + y * stride + a;
+            if (iy < 0 || iy >= in.H) continue;
+            for (int b = 0; b < size; ++b) {
+                const int ix = off + x * stride + b;
+                if (ix < 0 || ix >= in.W) continue;
+                const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(tv_px<T>(in, n, iy, ix)) + ch);
+                const T *v = reinterpret_cast<const T *>(&raw);
+#pragma unroll
+                for (int k = 0; k < V; ++k) { const float f = to_f32(v[k]); m[k] = (f > m[k]) ? f : m[k]; }
+            }
+        }
+        uint4 o;
+        T *ov = reinterpret_cast<T *>(&o);
+#pragma unroll
+        for (int k = 0; k < V; ++k) ov[k] = from_f32<T>(m[k]);
+        reinterpret_cast<uint4 *>(tv_px<T>(out, n, y, x))[ch] = o;
+    }
+}
+
 // upsample_cpu forward (reference yolov2_forward_network.c:380-394): out = scale * in[y/stride][x/stride]
 template <typename T>
 __global__ void k_upsample(TV in, TV out, int stride, float scale) {
