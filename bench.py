@@ -50,46 +50,60 @@ def conv_flops(sections, batch):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML every ~5 ms DURING the timed region (the nvidia-smi recipe of
+    B200_PROFILING.md is too coarse for a ~0.2 s region); falls back to `nvidia-smi -lms` when pynvml is missing."""
+    REASONS = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.gpu, self.samples, self.stop_flag, self.thread, self.max_mhz = gpu_index, [], False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[0].isdigit() else self.gpu
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), [t.strip() for t in line.split(",")]))
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        try:
+                            mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        except Exception:
+                            mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.samples.append((time.time(), float(mhz), int(mask)))
+                    except Exception:
+                        pass
+                    time.sleep(0.004)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.thread = None
 
     def stop(self, t0, t1):
-        if self.proc:
-            time.sleep(0.15)
-            self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ts, r in self.rows:
-            if len(r) < 8 or not (t0 - 0.05 <= ts <= t1 + 0.2):
-                continue
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=1.0)
+        sel = [(m, k) for ts, m, k in self.samples if t0 <= ts <= t1]
+        if not sel:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        reasons = sorted(name for name, bit in self.REASONS.items() if any(k & bit for _, k in sel))
+        return {"sm_mhz": float(np.median([m for m, _ in sel])), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sel)}
+
+
+def traffic_per_launch(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per k_conv_tc launch, averaged over the launches of one step, from
+    the committed ncu capture (profiles/r01_traffic.json, made with tools/ncu_traffic.sh); None when not captured."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        d = json.load(open(p))
+        return d.get(workload, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -294,7 +308,7 @@ def main():
             ach = fl / tsum / 1e12
             peak = peaks.get("bf16_tflops_sustained", 1400.0)
             roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": ach / peak, "traffic": None, "launches": len(by[dom]),
+                    "frac": ach / peak, "traffic": traffic_per_launch(args.workload), "launches": len(by[dom]),
                     "avg_launch_ms": tsum * 1e3 / len(by[dom]), "flops_per_launch": fl / len(by[dom]),
                     "share_of_step": tsum * 1e3 / sum(t for _, _, t in prof), "peak_source": src + " (sustained)"}
 
@@ -333,7 +347,7 @@ def main():
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "yb_network_submit/collect (3 batches in flight, pinned host buffers)",
                     "sync_predict_value": batch * world / t_sync, "sync_predict_ms": t_sync * 1e3},
-            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches": launches_per_step * args.steps * world,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "tflops": conv_flops(secs, batch * world) * args.steps / (ms_total * 1e-3) / 1e12,
         }
