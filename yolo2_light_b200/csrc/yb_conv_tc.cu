@@ -46,9 +46,12 @@ struct TcParams {
     int num_tiles;
     int num_work;             // work items of the persistent loop: num_tiles (CG=1) or pairs of m-tiles x nt (CG=2)
     int cg;                   // 1, or 2 = CTA pairs (cta_group::2)
-    int kind;                 // 0: bf16 x bf16 -> f32 (kind::f16);  1: s8 x s8 -> s32 (kind::i8), exact requantising epilogue
+    int kind;                 // 0: bf16 x bf16 -> f32 (kind::f16);  1: s8 x s8 -> s32 (kind::i8), exact requantising epilogue;
+                              // 2: XNOR layer as +-1 s8 on kind::i8 (dot = 2*count - K exactly), reference float epilogue
     int kk;                   // MMAs per K-block (BK bytes / 32)
     float alpha1;             // INT8: R_MULT / (input_mult * weights_mult)
+    const float *mean;        // kind 2 (XNOR as +-1 s8): per-filter mean |w|; out = (float)dot * mean + bias
+    int xK;                   // kind 2: true K (size*size*C) for the raw popcount dump: count = (dot + K) / 2
     int *acc_out;             // INT8: optional raw s32 accumulators, NCHW (tests)
     int PR, row_off;          // merged-row pitch per image; output row = (J % PR) - row_off
     int OH, OW, OHp, OWp;
@@ -335,7 +338,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         uint64_t bdesc = hi | (uint64_t)((((b_base + (uint32_t)j * b_bytes) & 0x3FFFFu) >> 4) | (1u << 16));
                         for (int k = 0; k < kk; ++k) {
                             if constexpr (CG == 2) umma2_bf16(d_tmem, adesc, bdesc, idesc, (uint32_t)((kb0 | j | k) != 0));
-                            else if (kind == 1) umma_i8(d_tmem, adesc, bdesc, idesc, (uint32_t)((kb0 | j | k) != 0));
+                            else if (kind != 0) umma_i8(d_tmem, adesc, bdesc, idesc, (uint32_t)((kb0 | j | k) != 0));
                             else umma_bf16(d_tmem, adesc, bdesc, idesc, (uint32_t)((kb0 | j | k) != 0));
                             adesc += 2; bdesc += 2;
                         }
@@ -389,7 +392,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         dst[g] = __ldg(reinterpret_cast<const uint4 *>(rrow + (size_t)(n0 + f0) * 2) + g);
                 }
             };
-            const bool coalesced = (p.out_bf16 && (cend - cbeg) >= 64 && !p.no_coalesce) || p.kind == 1;
+            const bool coalesced = (p.out_bf16 && (cend - cbeg) >= 64 && !p.no_coalesce) || p.kind != 0;
             if (!coalesced) {
                 if (cbeg < cend) load_res(cbeg, rv[0]);
                 if (cend - cbeg > 32) load_res(cbeg + 32, rv[1]);
@@ -444,6 +447,37 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 }
             };
 
+            if (p.kind == 2) {
+                // ---- XNOR as +-1 int8: acc == 2*count - K (exact); out = act((float)acc * mean + bias) in the reference's
+                // float op order (additionally.c:1531, yolov2_forward_network.c:243-261)
+                float *orow_f = reinterpret_cast<float *>(orow);
+                for (int f0 = cbeg; f0 < cend; f0 += 32) {
+                    uint32_t v0[32];
+                    tmem_ld32(taddr + (uint32_t)f0, v0);
+                    tmem_ld_wait();
+                    if (!valid) continue;
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        if (n0 + f0 + g * 4 >= p.n_store) break;
+                        float y[4];
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            const int f = n0 + f0 + g * 4 + h;
+                            float t = __fmul_rn((float)(int)v0[g * 4 + h], (f < p.n) ? __ldg(p.mean + f) : 0.f);
+                            t = __fadd_rn(t, bs[f0 + g * 4 + h]);
+                            y[h] = act_exact(t, p.act);
+                        }
+                        *reinterpret_cast<float4 *>(orow_f + n0 + f0 + g * 4) = make_float4(y[0], y[1], y[2], y[3]);
+                    }
+                    if (p.acc_out) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int f = n0 + f0 + j;
+                            if (f < p.n) p.acc_out[(((size_t)img * p.n + f) * p.OH + oy) * p.OW + ox] = ((int)v0[j] + p.xK) / 2;
+                        }
+                    }
+                }
+            } else
             if (p.kind == 1) {
                 // ---- INT8: exact requantisation of the reference (yolov2_forward_network_quantized.c:474-490, :598-627):
                 // q16 = clamp(+-32767, acc / 32) [C truncating division]; y = (float)q16 * ALPHA1; y += bias; leaky: y / 10.
@@ -647,9 +681,9 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
     TcPlan *plan = new TcPlan();
     memset(plan, 0, sizeof(*plan));
     TcParams &p = plan->p;
-    const int esz = kind == 1 ? 1 : 2;                       // operand element size
-    const int cin = kind == 1 ? in.ldc : l.c;                // INT8: channels padded with zeros in both operands
-    const int BK = kind == 1 ? pick_bk_i8(cin) : pick_bk(l.c), BN = pick_bn(l.n);
+    const int esz = kind != 0 ? 1 : 2;                       // operand element size
+    const int cin = kind != 0 ? in.ldc : l.c;                // s8: channels padded with zeros in both operands
+    const int BK = kind != 0 ? pick_bk_i8(cin) : pick_bk(l.c), BN = pick_bn(l.n);
     p.kind = kind; p.alpha1 = alpha1; p.acc_out = acc_out;
     p.kk = BK * esz / 32;
     const bool s2 = l.stride == 2;
@@ -692,7 +726,7 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
     // UMMA instruction descriptor (kind::f16): D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TC_BM * p.cg) >> 4) << 24);
     // kind::i8: D = s32 (2 at bit 4), A = B = signed 8 bit (1 at bits 7 / 10)
-    if (kind == 1) p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    if (kind != 0) p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     // smem descriptor high word: SBO (8 rows * row bytes) >> 4 at bits 32..45, version 1 at bit 46, swizzle at 61..63
     const uint32_t row_bytes = (uint32_t)(BK * esz);
     const uint32_t layout = row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;
@@ -715,7 +749,7 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
     const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                  : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
     EncodeTiledFn enc = encode_fn();
-    const CUtensorMapDataType dtype = kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const CUtensorMapDataType dtype = kind != 0 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     CUresult r;
     if (!s2) {
         // activation view (c, x_padded, merged padded rows)
@@ -784,6 +818,17 @@ void *tc_make_plan_i8(const Layer &l, const TV &q, const TV &out, const void *d_
                       float alpha1, int *acc_out) {
     TV none{};
     return make_plan_common(1, l, q, out, false, none, false, ACT_LINEAR, d_weights_s8, ldn, d_bias, alpha1, acc_out);
+}
+
+// XNOR layer mapped onto kind::i8: activations and weights as +-1 bytes, so the s32 accumulator is 2*count - K.
+void *tc_make_plan_xnor(const Layer &l, const TV &q, const TV &out, const void *d_weights_pm1, int ldn, const float *d_bias,
+                        const float *d_mean, int *counts_out) {
+    TV none{};
+    TcPlan *plan = reinterpret_cast<TcPlan *>(
+        make_plan_common(2, l, q, out, false, none, false, ACT_LINEAR, d_weights_pm1, ldn, d_bias, 0.f, counts_out));
+    plan->p.mean = d_mean;
+    plan->p.xK = l.size * l.size * l.c;
+    return plan;
 }
 
 void tc_launch(void *vp, cudaStream_t s) {

@@ -17,6 +17,9 @@ void *tc_make_plan(const Layer &l, const TV &in, const TV &out, bool out_bf16, c
 int tc_i8_supported(const Layer &l, const TV &q, const TV &out);
 void *tc_make_plan_i8(const Layer &l, const TV &q, const TV &out, const void *d_weights_s8, int ldn, const float *d_bias,
                       float alpha1, int *acc_out);
+// XNOR layer as +-1 s8 on kind::i8 (q: s8 activation with -1 borders)
+void *tc_make_plan_xnor(const Layer &l, const TV &q, const TV &out, const void *d_weights_pm1, int ldn, const float *d_bias,
+                        const float *d_mean, int *counts_out);
 void tc_launch(void *plan, cudaStream_t s);
 void tc_free_plan(void *plan);
 

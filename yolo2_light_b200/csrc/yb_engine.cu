@@ -196,6 +196,13 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
     };
 
     const auto cons = consumers_of(*net);
+    // XNOR layers with enough channels run on the tensor cores as +-1 int8 (dot == 2*count - K, exact); the small
+    // ones stay on the popcount kernels.  YB_XNOR_TC=0 forces popcount everywhere.
+    auto xnor_on_tc = [&](const Layer &l) {
+        const char *ev = getenv("YB_XNOR_TC");
+        if (ev && ev[0] == '0') return false;
+        return l.xnor && l.c % 32 == 0 && l.c >= 64 && l.size == 3 && l.stride == 1 && l.pad == 1 && l.n >= 8;
+    };
 
     // ---- fusion plan: conv i + same-shape shortcut i+1 whose only reader is that shortcut -------------
     std::vector<int> fused_into(nl, -1);   // conv i writes layer fused_into[i]'s output
@@ -275,7 +282,11 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
         const Layer &l = net->layers[i];
         if (l.type != YB_CONVOLUTIONAL) continue;
         const int v = conv_variant(i);
-        if (v == 1) {
+        if (v == 1 && xnor_on_tc(l)) {
+            side_ld[i] = l.c;   // +-1 bytes
+            side_off[i] = act_total;
+            act_total += align_up(tv_bytes(B, l.h, l.w, side_ld[i], P, DT_S8), 1024);
+        } else if (v == 1) {
             side_ld[i] = (l.c + 31) / 32;
             side_off[i] = act_total;
             act_total += align_up(tv_bytes(B, l.h, l.w, side_ld[i], P, DT_BITS), 1024);
@@ -289,6 +300,11 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
     CUDA_OK(cudaMalloc(&e->act_arena, act_total));
     CUDA_OK(cudaMemsetAsync(e->act_arena, 0, act_total, e->stream));   // zero borders, once
 
+    for (int i = 0; i < nl; ++i) {   // +-1 activation buffers: borders are -1 (out-of-image taps count as -1)
+        const Layer &l = net->layers[i];
+        if (l.type == YB_CONVOLUTIONAL && conv_variant(i) == 1 && xnor_on_tc(l))
+            CUDA_OK(cudaMemsetAsync(e->act_arena + side_off[i], 0xFF, tv_bytes(B, l.h, l.w, side_ld[i], P, DT_S8), e->stream));
+    }
     e->in0 = make_tv(e->act_arena + in0_off, B, net->h, net->w, net->c, net->c, P, ADT, 0);
     e->out_tv.assign(nl, TV{});
     for (int i = 0; i < nl; ++i) {
@@ -384,6 +400,18 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                         for (int t = 0; t < taps; ++t)
                             dst[((size_t)t * l.c + c) * w.ldw + f] = l.weights[((size_t)f * l.c + c) * taps + t];
             }
+        } else if (v == 1 && xnor_on_tc(l)) {
+            // +-1 bytes [ldn][taps][C]: +1 where w > 0, -1 otherwise; padded filter rows stay 0
+            w.cpad = l.c;
+            w.ldn = (int)align_up(l.n, 64);
+            w.w_s8 = reserve((size_t)w.ldn * taps * l.c);
+            int8_t *dst = reinterpret_cast<int8_t *>(&hostw[w.w_s8]);
+            for (int f = 0; f < l.n; ++f)
+                for (int c = 0; c < l.c; ++c)
+                    for (int t = 0; t < taps; ++t)
+                        dst[((size_t)f * taps + t) * l.c + c] = l.weights[((size_t)f * l.c + c) * taps + t] > 0 ? 1 : -1;
+            w.mean = reserve(sizeof(float) * align_up(l.n, 64));
+            memcpy(&hostw[w.mean], l.mean_arr.data(), sizeof(float) * l.n);
         } else if (v == 1) {
             // sign bits [ldn][taps][CW]; bit = (w > 0) (binarize_weights additionally.c:113 + float_to_bit :1536)
             const int CW = (l.c + 31) / 32;
@@ -522,12 +550,38 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                 }
             } else if (v == 1) {
                 if (in_dt != DT_F32 || odt != DT_F32) fatal_throw("engine: xnor path needs f32 activations");
+                int32_t *cnt_dbg = nullptr;
+                if (opt.keep_counts) {
+                    e->counts_count[i] = (size_t)B * l.n * l.out_h * l.out_w;
+                    CUDA_OK(cudaMalloc(&e->d_counts[i], e->counts_count[i] * sizeof(int32_t)));
+                    cnt_dbg = e->d_counts[i];
+                }
+                const bool in_vec = (tin.ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(tin.base) & 15) == 0;
+                if (xnor_on_tc(l) && in_vec) {
+                    TV q = make_tv(e->act_arena + side_off[i], B, l.h, l.w, l.c, l.c, P, DT_S8, 0);
+                    if (tc_i8_supported(l, q, tout)) {
+                        const int g = grid_for((long)B * l.h * l.w * (l.c / 16));
+                        e->ops.push_back(Op{OP_BINARIZE, i, [tin, q, g](cudaStream_t s) { k_binarize_s8<<<g, 256, 0, s>>>(tin, q); }});
+                        void *plan = tc_make_plan_xnor(l, q, tout, e->w_arena + cw[i].w_s8, cw[i].ldn,
+                                                       reinterpret_cast<const float *>(e->w_arena + cw[i].bias),
+                                                       reinterpret_cast<const float *>(e->w_arena + cw[i].mean), cnt_dbg);
+                        e->tc_plans.push_back(plan);
+                        e->ops.push_back(Op{OP_CONV_TC_I8, i, [plan](cudaStream_t s) { tc_launch(plan, s); }});
+                        break;
+                    }
+                    fatal_throw("engine: xnor tensor-core layer not supported by the i8 tile");
+                }
                 const int CW = side_ld[i];
                 TV bits = make_tv(e->act_arena + side_off[i], B, l.h, l.w, CW, CW, P, DT_BITS, 0);
                 {
-                    const long total = (long)B * l.h * l.w * CW * 32;
-                    const int g = grid_for(total);
-                    e->ops.push_back(Op{OP_BINARIZE, i, [tin, bits, g](cudaStream_t s) { k_binarize<float><<<g, 256, 0, s>>>(tin, bits); }});
+                    if (in_vec) {
+                        const int g = grid_for((long)B * l.h * l.w * CW);
+                        e->ops.push_back(Op{OP_BINARIZE, i, [tin, bits, g](cudaStream_t s) { k_binarize_vec<float><<<g, 256, 0, s>>>(tin, bits); }});
+                    } else {
+                        const long total = (long)B * l.h * l.w * CW * 32;
+                        const int g = grid_for(total);
+                        e->ops.push_back(Op{OP_BINARIZE, i, [tin, bits, g](cudaStream_t s) { k_binarize<float><<<g, 256, 0, s>>>(tin, bits); }});
+                    }
                 }
                 XnorP p{};
                 p.bits = bits; p.out = tout;
@@ -536,11 +590,17 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                 p.bias = reinterpret_cast<const float *>(e->w_arena + cw[i].bias);
                 p.n = l.n; p.size = l.size; p.pad = l.pad; p.K = l.size * l.size * l.c;
                 p.padbits = (CW * 32 - l.c) * l.size * l.size;
-                p.act = l.activation; p.M = M; p.counts = nullptr;
-                if (opt.keep_counts) {
-                    e->counts_count[i] = (size_t)B * l.n * l.out_h * l.out_w;
-                    CUDA_OK(cudaMalloc(&e->d_counts[i], e->counts_count[i] * sizeof(int32_t)));
-                    p.counts = e->d_counts[i];
+                p.act = l.activation; p.M = M; p.counts = cnt_dbg;
+                if (CW <= 2 && l.size == 3 && (size_t)l.n * 9 * CW * 4 <= 40 * 1024 && tout.ldc % 4 == 0) {
+                    // small K: one thread per pixel, all filters (weights broadcast from shared memory)
+                    const unsigned gsm = (unsigned)((M + 127) / 128);
+                    const size_t smem = (size_t)l.n * 9 * CW * 4;
+                    const int cw1 = CW;
+                    e->ops.push_back(Op{OP_CONV_XNOR, i, [p, gsm, smem, cw1](cudaStream_t s) {
+                        if (cw1 == 1) k_conv_xnor_smallk<1><<<gsm, 128, smem, s>>>(p);
+                        else k_conv_xnor_smallk<2><<<gsm, 128, smem, s>>>(p);
+                    }});
+                    break;
                 }
                 dim3 grid((unsigned)((M + 63) / 64), (unsigned)((l.n + 63) / 64));
                 e->ops.push_back(Op{OP_CONV_XNOR, i, [p, grid](cudaStream_t s) { k_conv_xnor<<<grid, 256, 0, s>>>(p); }});

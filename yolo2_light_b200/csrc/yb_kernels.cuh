@@ -241,8 +241,11 @@ __global__ void __launch_bounds__(128) k_conv_stem(const float *__restrict__ in,
             op[g] = v;
         }
     } else {
+        float4 *op = reinterpret_cast<float4 *>(o);   // NF*4 bytes per pixel, 16-byte aligned (ldc % 4 == 0)
 #pragma unroll
-        for (int f = 0; f < NF; ++f) o[f] = from_f32<TOut>(act_exact(acc[f] + sw.b[f], act));
+        for (int g = 0; g < NF / 4; ++g)
+            op[g] = make_float4(act_exact(acc[g * 4 + 0] + sw.b[g * 4 + 0], act), act_exact(acc[g * 4 + 1] + sw.b[g * 4 + 1], act),
+                                act_exact(acc[g * 4 + 2] + sw.b[g * 4 + 2], act), act_exact(acc[g * 4 + 3] + sw.b[g * 4 + 3], act));
     }
 }
 
@@ -272,10 +275,6 @@ __global__ void k_binarize(TV in, TV bits /* C = words per pixel */) {
     }
 }
 
-// XNOR bit-GEMM convolution, 3x3 / stride 1 / pad 1: count = sum_taps popc(~(a ^ w)) - (pad bits), then
-// out = act((2*count - K) * mean[f] + bias[f]) evaluated in the reference's float op order
-// (additionally.c:1531, yolov2_forward_network.c:243-261).  64 pixels x 64 filters per CTA, 4x4 per thread,
-// K streamed through shared memory in 8-word slices with 128-bit loads.
 struct XnorP {
     TV bits;                  // input bits, C = words per pixel (CW)
     TV out;                   // f32
@@ -288,6 +287,105 @@ struct XnorP {
     long M;
     int32_t *counts;          // optional raw popcounts, NCHW (tests)
 };
+
+// thread-per-(pixel, word) variant: each thread reads its 32 (or fewer) channels with 16-byte loads -- far fewer,
+// fatter threads than the ballot version; used whenever the channel vector is 16-byte aligned.
+template <typename TIn>
+__global__ void k_binarize_vec(TV in, TV bits) {
+    const int CW = bits.C;
+    const long total = (long)in.N * in.H * in.W * CW;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int wd = (int)(i % CW);
+        const long pxl = i / CW;
+        const int x = (int)(pxl % in.W);
+        const int y = (int)((pxl / in.W) % in.H);
+        const int n = (int)(pxl / ((long)in.W * in.H));
+        const float4 *src = reinterpret_cast<const float4 *>(tv_px<float>(in, n, y, x) + wd * 32);
+        const int nch = min(32, in.C - wd * 32);
+        uint32_t m = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (q * 4 < nch) {
+                const float4 v = __ldg(src + q);
+                m |= (uint32_t)(v.x > 0.f) << (q * 4) | (uint32_t)(v.y > 0.f) << (q * 4 + 1) |
+                     (uint32_t)(v.z > 0.f) << (q * 4 + 2) | (uint32_t)(v.w > 0.f) << (q * 4 + 3);
+            }
+        }
+        tv_px<uint32_t>(bits, n, y, x)[wd] = m;
+    }
+}
+
+// sign(+-1) as s8 for the tensor-core XNOR mapping: +1 where x > 0, -1 otherwise (border bytes are pre-set to -1,
+// the reference's "out-of-image taps are -1" rule).  16 channels per thread.
+static __global__ void k_binarize_s8(TV in, TV q) {
+    const int groups = in.C >> 4;
+    const long total = (long)in.N * in.H * in.W * groups;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % groups);
+        const long pxl = i / groups;
+        const int x = (int)(pxl % in.W);
+        const int y = (int)((pxl / in.W) % in.H);
+        const int n = (int)(pxl / ((long)in.W * in.H));
+        const float4 *src = reinterpret_cast<const float4 *>(tv_px<float>(in, n, y, x) + g * 16);
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float4 v = __ldg(src + k);
+            w[k] = (v.x > 0.f ? 0x01u : 0xFFu) | (v.y > 0.f ? 0x01u : 0xFFu) << 8 | (v.z > 0.f ? 0x01u : 0xFFu) << 16 |
+                   (v.w > 0.f ? 0x01u : 0xFFu) << 24;
+        }
+        reinterpret_cast<uint4 *>(tv_px<int8_t>(q, n, y, x))[g] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// XNOR convolution for small K (one or two words per tap): one thread per output pixel keeps its 9 x CW input
+// words in registers and walks all filters, whose sign words sit in shared memory (broadcast reads).
+template <int CW>
+__global__ void __launch_bounds__(128) k_conv_xnor_smallk(XnorP p) {
+    extern __shared__ uint32_t wsm[];            // [n][9*CW]
+    constexpr int KW = 9 * CW;
+    for (int i = threadIdx.x; i < p.n * KW; i += blockDim.x) wsm[i] = p.w[i];
+    __syncthreads();
+    const int H = p.out.H, W = p.out.W;
+    const long m = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (m >= p.M) return;
+    const int x = (int)(m % W);
+    const int y = (int)((m / W) % H);
+    const int n = (int)(m / ((long)W * H));
+    uint32_t a[KW];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const uint32_t *src = tv_px<uint32_t>(p.bits, n, y + t / 3 - 1, x + t % 3 - 1);   // border words are 0 (== -1)
+#pragma unroll
+        for (int c = 0; c < CW; ++c) a[t * CW + c] = src[c];
+    }
+    float *o = tv_px<float>(p.out, n, y, x);
+    for (int f0 = 0; f0 < p.n; f0 += 4) {
+        float r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int f = f0 + j;
+            int cnt = 0;
+            if (f < p.n) {
+                const uint32_t *wf = wsm + f * KW;
+#pragma unroll
+                for (int k = 0; k < KW; ++k) cnt += __popc(~(a[k] ^ wf[k]));
+            }
+            const int count = cnt - p.padbits;
+            if (p.counts && f < p.n) p.counts[(((size_t)n * p.n + f) * H + y) * W + x] = count;
+            float v = (f < p.n) ? __fmul_rn((float)(2 * count - p.K), p.mean[f]) : 0.f;
+            v = (f < p.n) ? __fadd_rn(v, p.bias[f]) : 0.f;
+            r[j] = act_exact(v, p.act);
+        }
+        if (f0 + 3 < p.n) *reinterpret_cast<float4 *>(o + f0) = make_float4(r[0], r[1], r[2], r[3]);
+        else for (int j = 0; j < 4 && f0 + j < p.n; ++j) o[f0 + j] = r[j];
+    }
+}
+
+// XNOR bit-GEMM convolution, 3x3 / stride 1 / pad 1: count = sum_taps popc(~(a ^ w)) - (pad bits), then
+// out = act((2*count - K) * mean[f] + bias[f]) evaluated in the reference's float op order
+// (additionally.c:1531, yolov2_forward_network.c:243-261).  64 pixels x 64 filters per CTA, 4x4 per thread,
+// K streamed through shared memory in 8-word slices with 128-bit loads.
 
 static __global__ void __launch_bounds__(256) k_conv_xnor(XnorP p) {
     constexpr int BM = 64, BN = 64, BKW = 8;
