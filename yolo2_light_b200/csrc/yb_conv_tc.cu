@@ -53,6 +53,8 @@ struct TcParams {
     const float *mean;        // kind 2 (XNOR as +-1 s8): per-filter mean |w|; out = (float)dot * mean + bias
     int xK;                   // kind 2: true K (size*size*C) for the raw popcount dump: count = (dot + K) / 2
     int *acc_out;             // INT8: optional raw s32 accumulators, NCHW (tests)
+    float *yolo_out;          // fused [yolo] layer (reference yolov2_forward_network.c:453-472): NCHW f32 destination, or null
+    int yolo_per;             // 4 + classes + 1
     int PR, row_off;          // merged-row pitch per image; output row = (J % PR) - row_off
     int OH, OW, OHp, OWp;
     int size, cblocks, kblocks;
@@ -256,6 +258,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map prefetch, bias ->
+    // smem: weights only) overlapped the tail of the previous kernel; from here on we touch activations it wrote.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
         // ======================= TMA producer (every CTA loads its own A rows and its share of B) ===========
@@ -436,6 +442,22 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         o.z = pack_bf16x2(x[g * 8 + 4], x[g * 8 + 5]);
                         o.w = pack_bf16x2(x[g * 8 + 6], x[g * 8 + 7]);
                         op[g] = o;
+                    }
+                } else if (p.yolo_out) {
+                    // detection head with the [yolo] layer fused: logistic on x, y, objectness and class entries (w, h stay
+                    // raw), written straight into the NCHW tensor the reference decoder reads -- the f32 NHWC copy of the
+                    // head and the separate yolo kernel disappear
+                    int e = (n0 + f0) % p.yolo_per;
+                    float *dst = p.yolo_out + (((size_t)img * p.n + (n0 + f0)) * p.OH + oy) * (size_t)p.OW + ox;
+                    const size_t plane = (size_t)p.OH * p.OW;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (n0 + f0 + j < p.n) {
+                            float v = x[j];
+                            if (e != 2 && e != 3) v = 1.f / (1.f + __expf(-v));
+                            dst[(size_t)j * plane] = v;
+                        }
+                        if (++e == p.yolo_per) e = 0;
                     }
                 } else {
                     float4 *op = reinterpret_cast<float4 *>(orow + (size_t)(n0 + f0) * 4);
@@ -652,6 +674,7 @@ struct TcPlan {
     TcParams p;
     int grid;
     size_t smem;
+    int pdl;
     char desc[96];
 };
 
@@ -783,6 +806,7 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    plan->pdl = (getenv("YB_NO_PDL") == nullptr) ? 1 : 0;
     plan->grid = (p.cg == 2) ? 2 * std::min(p.num_work, sms / 2) : std::min(p.num_tiles, sms);
     if (getenv("YB_TC_STATS")) {
         cudaMalloc(&p.stats, sizeof(unsigned long long) * 8 * plan->grid);
@@ -814,6 +838,12 @@ int tc_i8_supported(const Layer &l, const TV &q, const TV &out) {
     if (l.activation != YB_LEAKY && l.activation != YB_LINEAR) return 0;
     return 1;
 }
+void tc_plan_fuse_yolo(void *vp, float *d_yolo_nchw, int classes) {
+    TcPlan *plan = reinterpret_cast<TcPlan *>(vp);
+    plan->p.yolo_out = d_yolo_nchw;
+    plan->p.yolo_per = 4 + classes + 1;
+}
+
 void *tc_make_plan_i8(const Layer &l, const TV &q, const TV &out, const void *d_weights_s8, int ldn, const float *d_bias,
                       float alpha1, int *acc_out) {
     TV none{};
@@ -833,18 +863,24 @@ void *tc_make_plan_xnor(const Layer &l, const TV &q, const TV &out, const void *
 
 void tc_launch(void *vp, cudaStream_t s) {
     TcPlan *plan = reinterpret_cast<TcPlan *>(vp);
-    if (plan->p.cg == 2) {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)plan->grid); cfg.blockDim = dim3(TC_THREADS);
-        cfg.dynamicSmemBytes = plan->smem; cfg.stream = s;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, k_conv_tc<2>, plan->tmA, plan->tmB, plan->p);
-    } else {
-        k_conv_tc<1><<<plan->grid, TC_THREADS, plan->smem, s>>>(plan->tmA, plan->tmB, plan->p);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)plan->grid); cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = plan->smem; cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (plan->pdl) {   // let this kernel's prologue start while the previous kernel drains
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
     }
+    if (plan->p.cg == 2) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    if (plan->p.cg == 2) cudaLaunchKernelEx(&cfg, k_conv_tc<2>, plan->tmA, plan->tmB, plan->p);
+    else cudaLaunchKernelEx(&cfg, k_conv_tc<1>, plan->tmA, plan->tmB, plan->p);
 }
 
 void tc_free_plan(void *vp) {

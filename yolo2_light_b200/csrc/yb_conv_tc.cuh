@@ -20,6 +20,8 @@ void *tc_make_plan_i8(const Layer &l, const TV &q, const TV &out, const void *d_
 // XNOR layer as +-1 s8 on kind::i8 (q: s8 activation with -1 borders)
 void *tc_make_plan_xnor(const Layer &l, const TV &q, const TV &out, const void *d_weights_pm1, int ldn, const float *d_bias,
                         const float *d_mean, int *counts_out);
+// fuse the following [yolo] layer into the (f32-output) plan: logistic + NCHW store in the epilogue
+void tc_plan_fuse_yolo(void *plan, float *d_yolo_nchw, int classes);
 void tc_launch(void *plan, cudaStream_t s);
 void tc_free_plan(void *plan);
 

@@ -220,6 +220,9 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
         }
     }
 
+    // ---- fusion plan: detection-head conv i + [yolo] i+1 (tensor-core path only; decided again when ops are emitted)
+    std::vector<char> yolo_fused(nl, 0);
+
     // ---- output placement --------------------------------------------------------------------------
     // pass 1: decide dtype + home of every layer output (own buffer, or a channel slice of a concat buffer)
     struct Home { int owner = -1; int coff = 0; int ldc = 0; };   // owner: layer whose buffer holds it
@@ -525,6 +528,11 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                                               e->w_arena + cw[i].w_bf16, cw[i].ldn,
                                               reinterpret_cast<const float *>(e->w_arena + cw[i].bias));
                     e->tc_plans.push_back(plan);
+                    if (opt.fuse && fused_into[i] < 0 && odt == DT_F32 && i + 1 < nl && net->layers[i + 1].type == YB_YOLO &&
+                        cons[i].size() == 1 && cons[i][0] == i + 1 && e->d_final[i + 1] && !getenv("YB_NO_YOLO_FUSE")) {
+                        tc_plan_fuse_yolo(plan, e->d_final[i + 1], net->layers[i + 1].classes);
+                        yolo_fused[i + 1] = 1;
+                    }
                     e->ops.push_back(Op{OP_CONV_TC, i, [plan](cudaStream_t s) { tc_launch(plan, s); }});
                 } else {
                     ConvP p{};
@@ -737,6 +745,7 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
             break;
         }
         case YB_YOLO: {
+            if (yolo_fused[i]) break;   // written by the head convolution's epilogue
             need_prev();
             float *dst = e->d_final[i];
             const int classes = l.classes;
