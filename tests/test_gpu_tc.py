@@ -79,8 +79,9 @@ def test_tc_every_layer_vs_oracle_on_bf16_inputs(size, batch, workdir):
     for i, l in enumerate(layers):
         if l["type_name"] != "CONVOLUTIONAL":
             continue
-        xin = x if i == 0 else got[i - 1]   # the stem kernel reads the caller's f32 NCHW image directly
         is_tc = "conv_tc" in kinds.get(i, [])
+        # the stem reads the caller's f32 NCHW image directly (tensor-core stem: rounds it to bf16 on the fly)
+        xin = (bf16_round(x) if is_tc else x) if i == 0 else got[i - 1]
         n_tc += is_tc
         w = bf16_round(l["weights"]) if is_tc else l["weights"]
         exp = port.conv_fp32(xin, w, l["biases"], l["n"], l["size"], l["stride"], l["pad"], l["activation"])

@@ -651,6 +651,122 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Stem convolution (3 input channels, 3x3 / stride 1 / pad 1) on the tensor cores.
+// K = 27 is padded to 32: every thread gathers the 3x3x3 window of ITS pixel straight from the caller's NCHW f32
+// image (the layout conversion is fused away), converts to bf16 and writes one 64-byte row of a 64B-swizzled A tile;
+// one thread then issues two tcgen05.mma (M=128, N=filters, K=16) and every thread drains its TMEM row through
+// bias + leaky-ReLU into bf16 NHWC.  No TMA (the gather is irregular), single-buffered, several CTAs per SM.
+// ------------------------------------------------------------------------------------------------------
+struct StemTcP {
+    const float *in;          // NCHW f32, set per call
+    char *out; int out_ldc;   // bf16 padded NHWC
+    const __nv_bfloat16 *w;   // [32 rows (filters, zero padded)][32 k] bf16, k = (ky,kx,c), k >= 27 zero
+    const float *bias;
+    int N, H, W, OHp, OWp, nf, act;
+    long npix;
+    int ntiles;
+};
+
+__global__ void __launch_bounds__(128) k_stem_tc(StemTcP p) {
+    __shared__ __align__(1024) uint8_t a_tile[128 * 64];
+    __shared__ __align__(1024) uint8_t b_tile[32 * 64];
+    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float bias_s[32];
+    const int t = threadIdx.x, warp = t >> 5;
+    const uint32_t a_addr = smem_u32(a_tile), b_addr = smem_u32(b_tile), bar = smem_u32(&mma_bar);
+    if (t < 32) bias_s[t] = (t < p.nf) ? p.bias[t] : 0.f;
+    {   // weights -> swizzled B tile (row f, 16-byte chunk j at f*64 + ((j ^ ((f>>1)&3)) << 4))
+        const int f = t >> 2, j = t & 3;
+        const uint4 v = *reinterpret_cast<const uint4 *>(p.w + f * 32 + j * 8);
+        *reinterpret_cast<uint4 *>(b_tile + f * 64 + ((j ^ ((f >> 1) & 3)) << 4)) = v;
+    }
+    if (t == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(32u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    // descriptors: K-major, 64-byte rows (SWIZZLE_64B = 4), SBO = 8 rows * 64 B, version 1
+    const uint64_t hi = (uint64_t)(((8u * 64u) >> 4) | (1u << 14) | (4u << 29)) << 32;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    uint32_t parity = 0;
+    const size_t plane = (size_t)p.H * p.W;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const long pix = (long)tile * 128 + t;
+        const bool ok = pix < p.npix;
+        int x = 0, y = 0, n = 0;
+        if (ok) { x = (int)(pix % p.W); y = (int)((pix / p.W) % p.H); n = (int)(pix / plane); }
+        // ---- gather 27 taps (k = (ky*3 + kx)*3 + c), pad to 32, as bf16
+        uint32_t packed[16];
+        {
+            const float *img = p.in + (size_t)n * 3 * plane;
+            float v[32];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int iy = y + ky - 1, ix = x + kx - 1;
+                    const bool in_img = ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        v[(ky * 3 + kx) * 3 + c] = in_img ? __ldg(img + (size_t)c * plane + (size_t)iy * p.W + ix) : 0.f;
+                }
+#pragma unroll
+            for (int k = 27; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) packed[k] = pack_bf16x2(v[2 * k], v[2 * k + 1]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4 *>(a_tile + t * 64 + ((j ^ ((t >> 1) & 3)) << 4)) =
+                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        __syncthreads();
+        if (t == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const uint64_t adesc = hi | (uint64_t)((((a_addr + 32u * k) & 0x3FFFFu) >> 4) | (1u << 16));
+                const uint64_t bdesc = hi | (uint64_t)((((b_addr + 32u * k) & 0x3FFFFu) >> 4) | (1u << 16));
+                umma_bf16(tmem_base, adesc, bdesc, idesc, (uint32_t)(k != 0));
+            }
+            umma_commit(bar);
+        }
+        mbar_wait(bar, parity, 9);
+        parity ^= 1u;
+        tc_fence_after();
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), acc);
+        tmem_ld_wait();
+        if (ok) {
+            char *orow = p.out + ((size_t)(n * p.OHp + y + 1) * p.OWp + x + 1) * (size_t)p.out_ldc * 2;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                if (g * 8 >= p.nf) break;
+                float r[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float a = __uint_as_float(acc[g * 8 + j]) + bias_s[g * 8 + j];
+                    r[j] = (p.act == ACT_LEAKY) ? fmaxf(a, 0.1f * a) : a;
+                }
+                reinterpret_cast<uint4 *>(orow)[g] = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]),
+                                                                pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
+            }
+        }
+        tc_fence_before();
+        __syncthreads();   // TMEM row drained and A tile consumed before the next tile overwrites them
+    }
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32u) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -860,6 +976,35 @@ void *tc_make_plan_xnor(const Layer &l, const TV &q, const TV &out, const void *
     plan->p.xK = l.size * l.size * l.c;
     return plan;
 }
+
+struct StemPlan { StemTcP p; int grid; };
+int tc_stem_supported(const Layer &l, const TV &out) {
+    return l.c == 3 && l.size == 3 && l.stride == 1 && l.pad == 1 && (l.n == 16 || l.n == 32) &&
+           (l.activation == YB_LEAKY || l.activation == YB_LINEAR) && out.base && out.ldc % 8 == 0 &&
+           (reinterpret_cast<uintptr_t>(out.base) & 15) == 0;
+}
+// d_w: device buffer of 32*32 bf16 ([filter][k], k = (ky,kx,c), zero padded), d_bias: device f32[>= n]
+void *tc_stem_make_plan(const Layer &l, const TV &out, const void *d_w, const float *d_bias) {
+    StemPlan *sp = new StemPlan();
+    memset(sp, 0, sizeof(*sp));
+    StemTcP &p = sp->p;
+    p.out = out.base; p.out_ldc = out.ldc; p.w = reinterpret_cast<const __nv_bfloat16 *>(d_w); p.bias = d_bias;
+    p.N = out.N; p.H = l.h; p.W = l.w; p.OHp = out.Hp; p.OWp = out.Wp; p.nf = l.n; p.act = l.activation;
+    p.npix = (long)out.N * l.h * l.w;
+    p.ntiles = (int)((p.npix + 127) / 128);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    sp->grid = std::min(p.ntiles, sms * 8);
+    return sp;
+}
+void tc_stem_launch(void *vp, const float *d_in_nchw, cudaStream_t s) {
+    StemPlan *sp = reinterpret_cast<StemPlan *>(vp);
+    StemTcP p = sp->p;
+    p.in = d_in_nchw;
+    k_stem_tc<<<sp->grid, 128, 0, s>>>(p);
+}
+void tc_stem_free_plan(void *vp) { delete reinterpret_cast<StemPlan *>(vp); }
 
 void tc_launch(void *vp, cudaStream_t s) {
     TcPlan *plan = reinterpret_cast<TcPlan *>(vp);

@@ -22,6 +22,11 @@ void *tc_make_plan_xnor(const Layer &l, const TV &q, const TV &out, const void *
                         const float *d_mean, int *counts_out);
 // fuse the following [yolo] layer into the (f32-output) plan: logistic + NCHW store in the epilogue
 void tc_plan_fuse_yolo(void *plan, float *d_yolo_nchw, int classes);
+// tensor-core stem (3-channel 3x3 from the caller's NCHW f32 image, bf16 NHWC out)
+int tc_stem_supported(const Layer &l, const TV &out);
+void *tc_stem_make_plan(const Layer &l, const TV &out, const void *d_w_32x32_bf16, const float *d_bias);
+void tc_stem_launch(void *plan, const float *d_in_nchw, cudaStream_t s);
+void tc_stem_free_plan(void *plan);
 void tc_launch(void *plan, cudaStream_t s);
 void tc_free_plan(void *plan);
 

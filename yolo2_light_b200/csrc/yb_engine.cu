@@ -74,6 +74,7 @@ struct Engine {
     std::vector<void *> tc_plans;      // opaque per-layer state of the tensor-core path (tensor maps)
     std::function<void(const float *, cudaStream_t)> first_op;   // consumes the caller's NCHW images (pointer varies per call)
     int first_kind = OP_INPUT, first_layer = -1;
+    void *stem_plan = nullptr;
     // ---- pipelined end-to-end path: H2D(k+1) | compute(k) | D2H(k-1) on three streams -----------------
     struct Slot {
         float *d_in = nullptr;
@@ -94,6 +95,7 @@ Engine::~Engine() {
     for (float *p : d_final) if (p) cudaFree(p);
     for (int32_t *p : d_counts) if (p) cudaFree(p);
     for (void *p : tc_plans) tc_free_plan(p);
+    if (stem_plan) tc_stem_free_plan(stem_plan);
     for (Slot &sl : slots) {
         if (sl.d_in) cudaFree(sl.d_in);
         for (float *p : sl.d_out) if (p) cudaFree(p);
@@ -441,6 +443,19 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                         dst[((size_t)f * taps + t) * w.cpad + c] = l.weights_int8[((size_t)f * l.c + c) * taps + t];
         }
     }
+    size_t stem_w_off = (size_t)-1;
+    {
+        const Layer &l0 = net->layers[0];
+        if (ADT == DT_BF16 && l0.type == YB_CONVOLUTIONAL && conv_variant(0) == 0 && l0.c == 3 && l0.size == 3 && l0.n <= 32) {
+            stem_w_off = reserve(sizeof(__nv_bfloat16) * 32 * 32);
+            __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(&hostw[stem_w_off]);
+            for (int i = 0; i < 32 * 32; ++i) dst[i] = __float2bfloat16_rn(0.f);
+            for (int f = 0; f < l0.n; ++f)
+                for (int c = 0; c < 3; ++c)
+                    for (int t = 0; t < 9; ++t)
+                        dst[f * 32 + t * 3 + c] = __float2bfloat16_rn(l0.weights[((size_t)f * 3 + c) * 9 + t]);
+        }
+    }
     e->w_bytes = align_up(std::max<size_t>(hostw.size(), 1024), 1024);
     CUDA_OK(cudaMalloc(&e->w_arena, e->w_bytes));
     if (opt.upload) CUDA_OK(cudaMemcpyAsync(e->w_arena, hostw.data(), hostw.size(), cudaMemcpyHostToDevice, e->stream));
@@ -461,7 +476,16 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                              l0.size == 3 && l0.stride == 1 && l0.pad == 1 && (l0.n == 16 || l0.n == 32) &&
                              fused_into[0] < 0 && e->out_tv[0].base && !getenv("YB_NO_STEM") &&
                              (e->out_dt[0] == DT_F32 || (e->out_tv[0].ldc % 8 == 0));
-        if (stem_ok) {
+        if (stem_ok && stem_w_off != (size_t)-1 && e->out_dt[0] == DT_BF16 && tc_stem_supported(l0, e->out_tv[0]) &&
+            !getenv("YB_NO_STEM_TC")) {
+            // tensor-core stem: gathers the 3x3x3 window from NCHW, K padded 27 -> 32
+            stem_fused = true;
+            void *sp = tc_stem_make_plan(l0, e->out_tv[0], e->w_arena + stem_w_off,
+                                         reinterpret_cast<const float *>(e->w_arena + cw[0].bias));
+            e->stem_plan = sp;
+            e->first_kind = OP_CONV_TC; e->first_layer = 0;
+            e->first_op = [sp](const float *din, cudaStream_t s) { tc_stem_launch(sp, din, s); };
+        } else if (stem_ok) {
             stem_fused = true;
             const TV tout = e->out_tv[0];
             const int act = l0.activation, H = l0.h, W = l0.w, nf = l0.n, odt = e->out_dt[0];
