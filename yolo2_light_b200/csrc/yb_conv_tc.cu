@@ -856,11 +856,15 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
     p.b_bytes = (uint32_t)((BN / p.cg) * BK * esz);   // per CTA
     // several K-blocks per stage when they are small: the single MMA-issuing thread pays a fixed barrier round
     // trip per stage, which dominated the C<=64 layers (profiles/r01_notes.md)
-    p.sps = (int)std::max<uint32_t>(1, std::min<uint32_t>(4, (64u * 1024u) / (p.a_bytes + p.b_bytes)));
+    const uint32_t sps_target = getenv("YB_TC_SPS_TARGET") ? (uint32_t)atoi(getenv("YB_TC_SPS_TARGET")) : 64u * 1024u;
+    p.sps = (int)std::max<uint32_t>(1, std::min<uint32_t>(4, sps_target / (p.a_bytes + p.b_bytes)));
+    if (p.cg == 2) p.sps = 1;   // CTA pairs: 32 KB stages, 6 deep -- finer stages beat fewer barrier round trips here
     if (getenv("YB_TC_SPS")) p.sps = std::max(1, atoi(getenv("YB_TC_SPS")));
+    if (getenv("YB_TC_SPS_CG2") && p.cg == 2) p.sps = std::max(1, atoi(getenv("YB_TC_SPS_CG2")));
     p.sps = std::min(p.sps, p.kblocks);
     p.stage_bytes = (uint32_t)p.sps * (p.a_bytes + p.b_bytes);
-    p.stages = (int)std::min<size_t>(8, (192 * 1024 - sizeof(float) * (size_t)p.nt * BN) / p.stage_bytes);
+    const size_t max_stages = getenv("YB_TC_MAX_STAGES") ? (size_t)atoi(getenv("YB_TC_MAX_STAGES")) : 8;
+    p.stages = (int)std::min<size_t>(max_stages, (192 * 1024 - sizeof(float) * (size_t)p.nt * BN) / p.stage_bytes);
     if (p.stages < 2) fatal_throw("tc plan: tile does not fit shared memory");
     // UMMA instruction descriptor (kind::f16): D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TC_BM * p.cg) >> 4) << 24);
