@@ -36,7 +36,7 @@ def _oracle_outs(net, x, q):
 
 
 # ---- exact f32 mode: every layer of every model family against the oracle ---------------------------------
-@pytest.mark.parametrize("name", ["tiny64", "v3_32", "spp32", "v2voc32", "tinyvoc64"])
+@pytest.mark.parametrize("name", ["tiny64", "v3_32", "spp32", "v2voc32", "tinyvoc64", "tiny_w96_h64", "v3_w64_h96"])
 def test_fp32_mode_every_layer(name, workdir):
     import yolo2_light_b200 as yb
     B = 2
@@ -239,6 +239,18 @@ def test_dropin_from_reference_prepared_layers(name, q, workdir):
         t2 = np.delete(theirs, 5, axis=1)
         b = t2[np.lexsort(t2[:, :4].T[::-1])]
         assert np.allclose(a[:, :5], b[:, :5], rtol=2e-3 if q else 1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("name,q", [("tiny_w96_h64", 0), ("tiny_w96_h64", 1), ("v3_w64_h96", 0)])
+def test_non_square_inputs_default_precision(name, q, workdir):
+    """H != W through the default (tensor-core where the shape allows) paths, batch 3 (odd)."""
+    B = 3
+    net = _load(name, workdir, B, q)
+    x = util.images(name, B)
+    net.predict(x, quantized=bool(q))
+    outs = _oracle_outs(net, x, q)
+    for i, o in net.detection_outputs().items():
+        assert util.rel_l2(o, outs[i].reshape(o.shape)) <= 3e-3, (name, q, i)
 
 
 def test_empty_and_edge_inputs(workdir):

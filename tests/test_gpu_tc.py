@@ -57,15 +57,18 @@ def _files(workdir, name, secs, seed):
     return cfg, wts
 
 
-@pytest.mark.parametrize("size,batch", [(64, 2), (96, 3)])
+@pytest.mark.parametrize("size,batch", [(64, 2), (96, 3), ((64, 160), 2), ((96, 32), 1)])
 def test_tc_every_layer_vs_oracle_on_bf16_inputs(size, batch, workdir):
     import yolo2_light_b200 as yb
     from oracle import port
-    cfg, wts = _files(workdir, f"tcnet{size}", tcnet(size), 21)
+    h, w = size if isinstance(size, tuple) else (size, size)
+    secs = tcnet(64)
+    secs[0][1]["height"], secs[0][1]["width"] = str(h), str(w)    # non-square variants exercise H != W tiling
+    cfg, wts = _files(workdir, f"tcnet{h}x{w}", secs, 21)
     net = yb.load_network(cfg, wts, batch=batch)
     net.set_precision(yb.YB_PREC_BF16_TC)
     net.set_option("fuse", 0)
-    x = cfgs.synthetic_images(batch, 3, size, size, seed=5)
+    x = cfgs.synthetic_images(batch, 3, h, w, seed=5)
     net.predict(x)
     prof = net.profile()
     kinds = {}

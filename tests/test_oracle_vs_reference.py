@@ -21,7 +21,8 @@ def _ref_and_port(name, workdir, quantized, batch=1):
 
 
 @pytest.mark.parametrize("name,quantized", [("tiny64", 0), ("tiny64", 1), ("xnor64", 0), ("v3_32", 0),
-                                            ("spp32", 0), ("v2voc32", 0), ("tinyvoc64", 1), ("v3_32", 1)])
+                                            ("spp32", 0), ("v2voc32", 0), ("tinyvoc64", 1), ("v3_32", 1),
+                                            ("tiny_w96_h64", 0), ("tiny_w96_h64", 1), ("v3_w64_h96", 0)])
 def test_whole_network_bit_exact(name, quantized, workdir):
     """Same cfg, same generated .weights, same image -> every layer output of the restatement equals the
     reference's l.output bit-for-bit (FP32 conv: identical k-ascending float accumulation; XNOR / INT8: exact

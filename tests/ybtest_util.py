@@ -19,6 +19,9 @@ ZOO = {
     "v3_32": (lambda: cfgs.slim(cfgs.yolov3, 4, 32, 32), 32, 13, 103),
     "spp32": (lambda: cfgs.slim(cfgs.yolov3_spp, 4, 32, 32), 32, 14, 104),
     "v2voc32": (lambda: cfgs.slim(cfgs.yolov2_voc, 4, 32, 32), 32, 15, 105),
+    # non-square inputs (H != W): name -> builder uses (width, height)
+    "tiny_w96_h64": (lambda: cfgs.slim(cfgs.yolov3_tiny, 2, 96, 64), (64, 96), 17, 107),
+    "v3_w64_h96": (lambda: cfgs.slim(cfgs.yolov3, 4, 64, 96), (96, 64), 18, 108),
     "tinyvoc64": (lambda: cfgs.slim(cfgs.tiny_yolo_voc, 2, 64, 64), 64, 16, 106),
 }
 
@@ -36,7 +39,8 @@ def model_files(name, workdir):
 
 def images(name, batch):
     _, size, _, iseed = ZOO[name]
-    return cfgs.synthetic_images(batch, 3, size, size, seed=iseed)
+    h, w = size if isinstance(size, tuple) else (size, size)
+    return cfgs.synthetic_images(batch, 3, h, w, seed=iseed)
 
 
 def have_ref():
