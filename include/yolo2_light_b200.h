@@ -137,6 +137,14 @@ float *yb_network_predict(yb_network *net, const float *input);
  * activation is not LINEAR; everything else as in yb_network_predict with f32 activations. */
 float *yb_network_predict_quantized(yb_network *net, const float *input);
 
+/* Input pipeline on the device: replaces load_image_stb's u8 -> float/255 conversion
+ * (src/additionally.c:3080-3103) + resize_image (src/additionally.c:3021-3064) + network_predict_*.
+ * images_hwc: net.batch interleaved 8-bit images (HWC, net.c channels, as stbi_load returns them), all w x h.
+ * The bilinear resize to the network size is bit-identical to the reference's (scalar build). */
+float *yb_network_predict_image_u8(yb_network *net, const unsigned char *images_hwc, int w, int h, int quantized);
+/* Diagnostic: the planar float input (batch*c*h*w) the device pipeline produced for the last call. */
+int    yb_network_fetch_input(yb_network *net, int quantized, float *dst);
+
 /* Pipelined form of the two calls above for throughput serving: yb_network_submit enqueues one batch (H2D of
  * `input` on a copy stream, the forward on the compute stream, D2H of the yolo/region tensors on a third stream)
  * and returns a ticket immediately; yb_network_collect blocks until that batch is done and points the layers'

@@ -59,6 +59,7 @@ def _load(kind: str):
     lib.refh_get_boxes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_int,
                                    C.POINTER(C.c_int)]
     lib.refh_set_quiet.argtypes = [C.c_int]
+    lib.refh_load_resize_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     if hasattr(lib, "refh_predict_b200"):
         lib.refh_predict_b200.restype = C.POINTER(C.c_float)
         lib.refh_predict_b200.argtypes = [C.c_void_p, C.c_void_p]
@@ -140,3 +141,13 @@ class RefNet:
         cl = C.c_int()
         n = self.lib.refh_get_boxes(self.h, w, h, thresh, nms, out.ctypes.data_as(C.c_void_p), max_out, C.byref(cl))
         return out[:min(n, max_out)]
+
+
+def load_resize_u8(img_hwc: np.ndarray, out_w: int, out_h: int, kind: str = "scalar") -> np.ndarray:
+    """The reference's load_image_stb conversion + resize_image on one u8 HWC image -> float32[c, out_h, out_w]."""
+    lib = _load(kind)
+    img = np.ascontiguousarray(img_hwc, dtype=np.uint8)
+    h, w, c = img.shape
+    out = np.empty((c, out_h, out_w), np.float32)
+    lib.refh_load_resize_u8(img.ctypes.data_as(C.c_void_p), w, h, c, out_w, out_h, out.ctypes.data_as(C.c_void_p))
+    return out

@@ -223,6 +223,26 @@ void refh_im2col(float *im, int c, int hgt, int w, int k, int stride, int pad, f
     im2col_cpu(im, c, hgt, w, k, stride, pad, col);   /* additionally.c:39 */
 }
 
+/* Image pipeline of the reference app: u8 HWC (what stbi_load returns) -> planar float /255. (load_image_stb,
+ * additionally.c:3080-3103) -> resize_image bilinear to the network size (additionally.c:3021-3064, only when the
+ * size differs, load_image :3066-3078).  out: float[c*out_h*out_w]. */
+void refh_load_resize_u8(const unsigned char *data, int w, int h, int c, int out_w, int out_h, float *out)
+{
+    image im = make_image(w, h, c);
+    int i, j, k;
+    for (k = 0; k < c; ++k)
+        for (j = 0; j < h; ++j)
+            for (i = 0; i < w; ++i)
+                im.data[i + w * j + w * h * k] = (float)data[k + c * i + c * w * j] / 255.;
+    if ((out_h && out_w) && (out_h != im.h || out_w != im.w)) {
+        image resized = resize_image(im, out_w, out_h);
+        free_image(im);
+        im = resized;
+    }
+    memcpy(out, im.data, sizeof(float) * (size_t)im.w * im.h * im.c);
+    free_image(im);
+}
+
 #ifdef YB_DROPIN
 /* drop-in check: the glue of integration/yolo2_light_b200_glue.c behind the reference's own host code */
 float *network_predict_b200(network net, float *input);

@@ -282,3 +282,51 @@ void yo_route_copy(const float *src, int batch, long src_size, long dst_outputs,
     for (int j = 0; j < batch; ++j)
         memcpy(dst + offset + j * dst_outputs, src + j * src_size, sizeof(float) * src_size);
 }
+
+/* Input pipeline of the reference app: load_image_stb's u8 HWC -> planar float /255.
+ * (additionally.c:3080-3103) followed by resize_image (additionally.c:3021-3064): two-pass bilinear, first along x
+ * into `part`, then along y; every product and sum rounded to float as written there; the last column / row copy the
+ * source edge.  No resize when the size already matches (load_image :3066-3078). */
+void yo_load_resize_u8(const unsigned char *data, int w, int h, int c, int out_w, int out_h, float *out)
+{
+    float *im = (float *)malloc(sizeof(float) * (size_t)w * h * c);
+    for (int k = 0; k < c; ++k)
+        for (int j = 0; j < h; ++j)
+            for (int i = 0; i < w; ++i)
+                im[i + w * j + (size_t)w * h * k] = (float)((double)(float)data[k + c * i + c * w * j] / 255.);
+    if (!(out_h && out_w) || (out_h == h && out_w == w)) {
+        memcpy(out, im, sizeof(float) * (size_t)w * h * c);
+        free(im);
+        return;
+    }
+    float *part = (float *)malloc(sizeof(float) * (size_t)out_w * h * c);
+    const float w_scale = (float)(w - 1) / (out_w - 1);
+    const float h_scale = (float)(h - 1) / (out_h - 1);
+    for (int k = 0; k < c; ++k)
+        for (int r = 0; r < h; ++r)
+            for (int cc = 0; cc < out_w; ++cc) {
+                float val;
+                if (cc == out_w - 1 || w == 1) {
+                    val = im[(w - 1) + w * r + (size_t)w * h * k];
+                } else {
+                    const float sx = cc * w_scale;
+                    const int ix = (int)sx;
+                    const float dx = sx - ix;
+                    val = (1 - dx) * im[ix + w * r + (size_t)w * h * k] + dx * im[ix + 1 + w * r + (size_t)w * h * k];
+                }
+                part[cc + out_w * r + (size_t)out_w * h * k] = val;
+            }
+    for (int k = 0; k < c; ++k)
+        for (int r = 0; r < out_h; ++r) {
+            const float sy = r * h_scale;
+            const int iy = (int)sy;
+            const float dy = sy - iy;
+            for (int cc = 0; cc < out_w; ++cc) {
+                float val = (1 - dy) * part[cc + out_w * iy + (size_t)out_w * h * k];
+                if (!(r == out_h - 1 || h == 1)) val += dy * part[cc + out_w * (iy + 1) + (size_t)out_w * h * k];
+                out[cc + out_w * r + (size_t)out_w * out_h * k] = val;
+            }
+        }
+    free(part);
+    free(im);
+}

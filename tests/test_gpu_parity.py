@@ -290,3 +290,23 @@ def test_true_dropin_behind_reference_host_code(name, q, workdir):
         assert util.rel_l2(net.output(i), cpu_out[i]) <= tol, (name, q, i)
     gpu_boxes = net.get_boxes(640, 480, 0.25, 0.45)
     assert abs(gpu_boxes.shape[0] - cpu_boxes.shape[0]) <= max(2, cpu_boxes.shape[0] // 50)
+
+
+@pytest.mark.parametrize("src_hw", [(48, 80), (64, 64), (97, 131), (200, 33)])
+def test_device_input_pipeline_bit_exact(src_hw, workdir):
+    """u8 HWC -> /255 -> resize_image on the device == the reference's load_image_stb + resize_image bit-for-bit
+    (oracle port, itself pinned to the reference in tests/test_oracle_vs_reference.py), then the same forward."""
+    import yolo2_light_b200 as yb
+    from oracle import port
+    name, B = "tiny64", 2
+    net = _load(name, workdir, B, 0, precision=yb.YB_PREC_FP32)
+    rng = np.random.default_rng(7)
+    imgs = rng.integers(0, 256, (B, src_hw[0], src_hw[1], 3), dtype=np.uint8)
+    net.predict_image_u8(imgs)
+    got = net.fetch_input()
+    exp = np.stack([port.load_resize_u8(imgs[b], net.w, net.h) for b in range(B)])
+    assert util.bits_equal(got, exp), float(np.abs(got - exp).max())
+    a = {i: o.copy() for i, o in net.detection_outputs().items()}
+    net.predict(exp)
+    for i, o in net.detection_outputs().items():
+        assert util.bits_equal(o, a[i])

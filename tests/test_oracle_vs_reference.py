@@ -61,3 +61,12 @@ def test_quantize_input_matches_reference_cast():
         s = ((i & 0xffff) ^ 0x8000) - 0x8000
         exp.append(max(-127, min(127, s)))
     assert q.tolist() == exp
+
+
+@pytest.mark.parametrize("shape", [(480, 640, 608, 608), (37, 53, 64, 96), (64, 64, 64, 64), (1, 7, 32, 32), (100, 1, 32, 32)])
+def test_image_pipeline_port_equals_reference(shape):
+    """u8 -> float/255 -> resize_image: the port against the reference's own functions, bit-for-bit."""
+    from oracle import port, ref
+    h, w, oh, ow = shape
+    img = np.random.default_rng(h * 1000 + w).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    assert util.bits_equal(port.load_resize_u8(img, ow, oh), ref.load_resize_u8(img, ow, oh))

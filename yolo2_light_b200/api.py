@@ -90,6 +90,8 @@ def lib():
         "yb_network_set_option": (C.c_int, [vp, C.c_char_p, C.c_int]),
         "yb_network_predict": (fp, [vp, vp]),
         "yb_network_predict_quantized": (fp, [vp, vp]),
+        "yb_network_predict_image_u8": (fp, [vp, vp, C.c_int, C.c_int, C.c_int]),
+        "yb_network_fetch_input": (C.c_int, [vp, C.c_int, vp]),
         "yb_network_submit": (C.c_int, [vp, vp, C.c_int]),
         "yb_network_collect": (C.c_int, [vp, C.c_int, C.c_int]),
         "yb_network_layer_output": (fp, [vp, C.c_int, ip]),
@@ -122,7 +124,7 @@ EXPORTED_SYMBOLS = [
     "yb_network_from_layers", "yb_free_network", "yb_network_num_layers", "yb_network_dims", "yb_network_layer",
     "yb_network_layer_outputs", "yb_network_input_calibration", "yb_set_batch_network", "yb_network_set_device",
     "yb_network_set_precision", "yb_network_set_option", "yb_network_predict", "yb_network_predict_quantized",
-    "yb_network_submit", "yb_network_collect", "yb_network_layer_output", "yb_network_forward_device", "yb_network_sync_outputs", "yb_network_fetch_layer",
+    "yb_network_predict_image_u8", "yb_network_fetch_input", "yb_network_submit", "yb_network_collect", "yb_network_layer_output", "yb_network_forward_device", "yb_network_sync_outputs", "yb_network_fetch_layer",
     "yb_network_fetch_counts", "yb_forward_convolutional_layer", "yb_network_weight_arena",
     "yb_network_last_launches", "yb_network_profile", "yb_op_kind_name", "yb_get_network_boxes", "yb_alloc_pinned",
     "yb_free_pinned",
@@ -228,6 +230,21 @@ class Network:
         p = f(self._h, x.ctypes.data_as(C.c_void_p))
         _check(bool(p))
         return self.layer_output(self.n - 1)
+
+    def predict_image_u8(self, images_hwc: np.ndarray, quantized: bool = False) -> np.ndarray:
+        """u8 HWC images [batch, h, w, c] of any size -> device-side /255 + bilinear resize (the reference's
+        load_image_stb + resize_image) -> forward."""
+        x = np.ascontiguousarray(images_hwc, dtype=np.uint8)
+        if x.ndim != 4 or x.shape[0] != self.batch or x.shape[3] != self.c:
+            raise YbError(f"predict_image_u8 wants [batch={self.batch}, h, w, c={self.c}] uint8, got {x.shape}")
+        p = lib().yb_network_predict_image_u8(self._h, x.ctypes.data_as(C.c_void_p), x.shape[2], x.shape[1], int(quantized))
+        _check(bool(p))
+        return self.layer_output(self.n - 1)
+
+    def fetch_input(self, quantized: bool = False) -> np.ndarray:
+        dst = np.empty((self.batch, self.c, self.h, self.w), np.float32)
+        _check(lib().yb_network_fetch_input(self._h, int(quantized), dst.ctypes.data_as(C.c_void_p)) == 0)
+        return dst
 
     def submit(self, images: np.ndarray, quantized: bool = False) -> int:
         """Pipelined predict: enqueue one batch, returns a ticket (see yb_network_submit)."""

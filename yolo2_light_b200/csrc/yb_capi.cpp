@@ -246,6 +246,27 @@ int yb_network_collect(yb_network *n, int ticket, int quantized) {
     YB_CATCH(-1)
 }
 
+float *yb_network_predict_image_u8(yb_network *n, const unsigned char *images_hwc, int w, int h, int quantized) {
+    YB_TRY
+    Network &net = n->net;
+    if (w <= 0 || h <= 0) fatal_throw("predict_image_u8: bad image size");
+    Engine *e = get_engine(n, quantized);
+    engine_upload_u8(e, images_hwc, w, h, net.c, net.w, net.h, nullptr);
+    engine_forward(e, nullptr, nullptr);
+    engine_download_outputs(e, &net, nullptr);
+    net.last_launches = engine_num_launches(e) + 1;
+    return net.layers.back().output;
+    YB_CATCH(nullptr)
+}
+/* diagnostic: the resized planar float images the device pipeline produced for the last predict_image_u8 */
+int yb_network_fetch_input(yb_network *n, int quantized, float *dst) {
+    YB_TRY
+    Engine *e = get_engine(n, quantized);
+    engine_fetch_input(e, dst);
+    return 0;
+    YB_CATCH(-1)
+}
+
 const float *yb_network_layer_output(const yb_network *n, int i, int *count) {
     if (i < 0 || i >= (int)n->net.layers.size()) return nullptr;
     if (count) *count = (int)n->net.layers[i].output_count;

@@ -75,6 +75,7 @@ struct Engine {
     std::function<void(const float *, cudaStream_t)> first_op;   // consumes the caller's NCHW images (pointer varies per call)
     int first_kind = OP_INPUT, first_layer = -1;
     void *stem_plan = nullptr;
+    unsigned char *d_u8 = nullptr; size_t u8_bytes = 0;   // staging of the caller's u8 images (device-side input pipeline)
     // ---- pipelined end-to-end path: H2D(k+1) | compute(k) | D2H(k-1) on three streams -----------------
     struct Slot {
         float *d_in = nullptr;
@@ -96,6 +97,7 @@ Engine::~Engine() {
     for (int32_t *p : d_counts) if (p) cudaFree(p);
     for (void *p : tc_plans) tc_free_plan(p);
     if (stem_plan) tc_stem_free_plan(stem_plan);
+    if (d_u8) cudaFree(d_u8);
     for (Slot &sl : slots) {
         if (sl.d_in) cudaFree(sl.d_in);
         for (float *p : sl.d_out) if (p) cudaFree(p);
@@ -831,6 +833,22 @@ void engine_upload_input(Engine *e, const float *host_input, void *stream) {
     CUDA_OK(cudaMemcpyAsync(e->d_input, host_input, e->input_count * sizeof(float), cudaMemcpyHostToDevice, s));
 }
 
+// u8 HWC images (all `w` x `h` x `c`) -> resized planar float in the engine's input staging buffer
+void engine_upload_u8(Engine *e, const unsigned char *host_u8, int w, int h, int c, int net_w, int net_h, void *stream) {
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    CUDA_OK(cudaSetDevice(e->opt.device));
+    const size_t bytes = (size_t)e->batch * w * h * c;
+    if (bytes > e->u8_bytes) {
+        if (e->d_u8) cudaFree(e->d_u8);
+        CUDA_OK(cudaMalloc(&e->d_u8, bytes));
+        e->u8_bytes = bytes;
+    }
+    CUDA_OK(cudaMemcpyAsync(e->d_u8, host_u8, bytes, cudaMemcpyHostToDevice, s));
+    const long total = (long)e->batch * c * net_h * net_w;
+    k_resize_u8_to_nchw<<<grid_for(total), 256, 0, s>>>(e->d_u8, e->batch, w, h, c, e->d_input, net_w, net_h);
+    CUDA_OK(cudaGetLastError());
+}
+
 void *engine_stream(Engine *e) { return e->stream; }
 
 void engine_forward(Engine *e, const void *d_input, void *stream) {
@@ -960,6 +978,12 @@ void engine_fetch_layer(Engine *e, Network *net, int layer, float *dst) {
     CUDA_OK(cudaMemcpyAsync(dst, tmp, count * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     CUDA_OK(cudaStreamSynchronize(e->stream));
     cudaFree(tmp);
+}
+
+void engine_fetch_input(Engine *e, float *dst) {
+    CUDA_OK(cudaSetDevice(e->opt.device));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    CUDA_OK(cudaMemcpy(dst, e->d_input, e->input_count * sizeof(float), cudaMemcpyDeviceToHost));
 }
 
 int engine_fetch_counts(Engine *e, int layer, int32_t *dst, size_t count) {

@@ -32,11 +32,13 @@ struct Engine;
 std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt);
 // d_input == nullptr: use the engine's staging buffer (filled by engine_upload_input)
 void engine_upload_input(Engine *e, const float *host_input, void *stream);
+void engine_upload_u8(Engine *e, const unsigned char *host_u8, int w, int h, int c, int net_w, int net_h, void *stream);
 void engine_forward(Engine *e, const void *d_input, void *stream);
 void engine_download_outputs(Engine *e, Network *net, void *stream);   // async D2H into pinned, then sync
 int engine_submit(Engine *e, const float *host_input);
 void engine_collect(Engine *e, Network *net, int ticket);
 void engine_fetch_layer(Engine *e, Network *net, int layer, float *dst);
+void engine_fetch_input(Engine *e, float *dst);
 int engine_fetch_counts(Engine *e, int layer, int32_t *dst, size_t count);
 void engine_weight_arena(Engine *e, void **ptr, size_t *bytes);
 int engine_num_launches(Engine *e);

@@ -75,6 +75,52 @@ __global__ void k_nhwc_to_nchw_f32(TV in, float *__restrict__ out) {
 }
 
 // ------------------------------------------------------------------------------------------------------
+// input pipeline of the reference app on the device: u8 HWC image (what stbi_load returns) ->
+// planar float /255. (load_image_stb, additionally.c:3080-3103) -> resize_image's two-pass bilinear to the network
+// size (additionally.c:3021-3064), fused: one thread per output element recomputes the two x-interpolated values it
+// needs.  Every product and sum is rounded to float exactly where the reference rounds (no FMA contraction), so the
+// result is bit-identical to the reference's scalar build.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float u8_to_unit(unsigned char v) { return (float)((double)(float)v / 255.0); }
+
+__device__ __forceinline__ float resize_part(const unsigned char *img, int w, int c, int k, int r, int cc, int out_w, float w_scale) {
+    // value of the reference's `part` image at (cc, r, k)
+    if (cc == out_w - 1 || w == 1) return u8_to_unit(img[k + c * (w - 1) + c * w * r]);
+    const float sx = __fmul_rn((float)cc, w_scale);
+    const int ix = (int)sx;
+    const float dx = __fsub_rn(sx, (float)ix);
+    const float a = u8_to_unit(img[k + c * ix + c * w * r]), b = u8_to_unit(img[k + c * (ix + 1) + c * w * r]);
+    return __fadd_rn(__fmul_rn(__fsub_rn(1.f, dx), a), __fmul_rn(dx, b));
+}
+
+static __global__ void k_resize_u8_to_nchw(const unsigned char *__restrict__ src, int n_img, int w, int h, int c,
+                                           float *__restrict__ dst, int out_w, int out_h) {
+    const long total = (long)n_img * c * out_h * out_w;
+    const bool same = (out_w == w && out_h == h);
+    const float w_scale = (float)(w - 1) / (float)(out_w - 1);
+    const float h_scale = (float)(h - 1) / (float)(out_h - 1);
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int cc = (int)(i % out_w);
+        const int r = (int)((i / out_w) % out_h);
+        const int k = (int)((i / ((long)out_w * out_h)) % c);
+        const int n = (int)(i / ((long)out_w * out_h * c));
+        const unsigned char *img = src + (size_t)n * w * h * c;
+        float val;
+        if (same) {
+            val = u8_to_unit(img[k + c * cc + c * w * r]);
+        } else {
+            const float sy = __fmul_rn((float)r, h_scale);
+            const int iy = (int)sy;
+            const float dy = __fsub_rn(sy, (float)iy);
+            val = __fmul_rn(__fsub_rn(1.f, dy), resize_part(img, w, c, k, iy, cc, out_w, w_scale));
+            if (!(r == out_h - 1 || h == 1))
+                val = __fadd_rn(val, __fmul_rn(dy, resize_part(img, w, c, k, iy + 1, cc, out_w, w_scale)));
+        }
+        dst[i] = val;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // generic FP32 convolution on CUDA cores (implicit GEMM, 64 pixels x 64 filters per CTA, 4x4 per thread).
 // Semantics: forward_convolutional_layer_cpu FP32 branch (reference yolov2_forward_network.c:204-261):
 // out = act(sum_{c,ky,kx} w*in + bias) with zero padding; optional fused shortcut (reference :443-449):
