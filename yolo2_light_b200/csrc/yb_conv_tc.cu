@@ -398,7 +398,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         dst[g] = __ldg(reinterpret_cast<const uint4 *>(rrow + (size_t)(n0 + f0) * 2) + g);
                 }
             };
-            const bool coalesced = (p.out_bf16 && (cend - cbeg) >= 64 && !p.no_coalesce) || p.kind != 0;
+            const bool coalesced = (p.out_bf16 && ((cend - cbeg) >= 64 || (cend - cbeg) == 32) && !p.no_coalesce) || p.kind != 0;
             if (!coalesced) {
                 if (cbeg < cend) load_res(cbeg, rv[0]);
                 if (cend - cbeg > 32) load_res(cbeg + 32, rv[1]);
@@ -607,6 +607,73 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     __syncwarp();
                     if (p.res && f0 + 64 < cend) res_to_stage(f0 + 64);   // next slab's residual in flight
                 }
+            } else if (p.out_bf16 && (cend - cbeg) == 32 && !p.no_coalesce) {
+                // ---- coalesced path for 32-column slabs (BN = 32 / 64): a row is 64 B of bf16; the warp's staging
+                // tile is 32 rows x 64 B (16-byte chunk j of row r at r*64 + ((j ^ ((r >> 1) & 3)) << 4)); one
+                // instruction moves 8 rows x 64 B.
+                const uint32_t stg = stg_base + (uint32_t)(warp - 2) * 4096u;
+                const int srow = lane >> 2, schunk = lane & 3;
+                const unsigned long long obase = (unsigned long long)(uintptr_t)orow;
+                const unsigned long long rbase = (unsigned long long)(uintptr_t)rrow;
+                const int vflag = valid ? 1 : 0;
+                auto stage_addr = [&](int row, int chunk) { return stg + (uint32_t)row * 64u + (uint32_t)((chunk ^ ((row >> 1) & 3)) << 4); };
+                const int f0 = cbeg;
+                if (p.res) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = i * 8 + srow;
+                        const unsigned long long rp = __shfl_sync(0xffffffffu, rbase, row);
+                        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                        if (rp && (n0 + f0 + schunk * 8) < p.n_store)
+                            v = __ldg(reinterpret_cast<const uint4 *>(rp + (size_t)(n0 + f0) * 2) + schunk);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(row, schunk)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                    }
+                }
+                uint32_t v0[32];
+                tmem_ld32(taddr + (uint32_t)f0, v0);
+                tmem_ld_wait();
+                float x[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float a0 = __uint_as_float(v0[j]) + bs[f0 + j];
+                    x[j] = leaky ? fmaxf(a0, 0.1f * a0) : a0;
+                }
+                if (p.res) {
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t w0, w1, w2, w3;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(stage_addr(lane, c)) : "memory");
+                        const uint32_t wv[4] = {w0, w1, w2, w3};
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            x[c * 8 + 2 * h] += __uint_as_float(wv[h] << 16);
+                            x[c * 8 + 2 * h + 1] += __uint_as_float(wv[h] & 0xffff0000u);
+                        }
+                    }
+                    if (leaky2) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.1f * x[j]);
+                    }
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(lane, c)),
+                                 "r"(pack_bf16x2(x[c * 8 + 0], x[c * 8 + 1])), "r"(pack_bf16x2(x[c * 8 + 2], x[c * 8 + 3])),
+                                 "r"(pack_bf16x2(x[c * 8 + 4], x[c * 8 + 5])), "r"(pack_bf16x2(x[c * 8 + 6], x[c * 8 + 7])) : "memory");
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = i * 8 + srow;
+                    const unsigned long long op = __shfl_sync(0xffffffffu, obase, row);
+                    const int ok = __shfl_sync(0xffffffffu, vflag, row);
+                    uint32_t w0, w1, w2, w3;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(stage_addr(row, schunk)) : "memory");
+                    if (ok && (n0 + f0 + schunk * 8) < p.n_store)
+                        *(reinterpret_cast<uint4 *>(op + (size_t)(n0 + f0) * 2) + schunk) = make_uint4(w0, w1, w2, w3);
+                }
+                __syncwarp();
             } else
             for (int f0 = cbeg; f0 < cend; f0 += 64) {
                 if (cend - f0 >= 64) {
