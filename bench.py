@@ -301,13 +301,22 @@ def main():
         dom = max(by, key=lambda k: sum(t for _, t in by[k]))
         peaks, src = measured_peaks()
         shapes = cfgs.conv_shapes(secs)
-        if dom in ("conv_tc", "conv_simt", "conv_tc_i8", "conv_int8", "conv_xnor"):
+        if dom in ("conv_tc", "conv_tc2", "conv_simt", "conv_tc_i8", "conv_int8", "conv_xnor"):
             fl = sum(2 * shapes[li]["n"] * shapes[li]["size"] ** 2 * shapes[li]["c"] * shapes[li]["out_h"] *
                      shapes[li]["out_w"] * batch for li, _ in by[dom])
             tsum = sum(t for _, t in by[dom]) * 1e-3
             ach = fl / tsum / 1e12
             peak = peaks.get("bf16_tflops_sustained", 1400.0)
-            roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+            kname = {"conv_tc2": "k_conv_tc<2> (tcgen05 cta_group::2 implicit-GEMM conv)",
+                     "conv_tc": "k_conv_tc<1> (tcgen05 implicit-GEMM conv)"}.get(dom, dom)
+            all_tc = [(li, t) for k in ("conv_tc", "conv_tc2") for li, t in by.get(k, [])]
+            fl_all = sum(2 * shapes[li]["n"] * shapes[li]["size"] ** 2 * shapes[li]["c"] * shapes[li]["out_h"] *
+                         shapes[li]["out_w"] * batch for li, _ in all_tc)
+            t_all = sum(t for _, t in all_tc) * 1e-3
+            roof = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                    "all_tensor_core_convs": {"achieved": fl_all / max(t_all, 1e-12) / 1e12, "launches": len(all_tc),
+                                              "frac": fl_all / max(t_all, 1e-12) / 1e12 / peak,
+                                              "share_of_step": t_all * 1e3 / sum(t for _, _, t in prof)},
                     "frac": ach / peak, "traffic": traffic_per_launch(args.workload), "launches": len(by[dom]),
                     "avg_launch_ms": tsum * 1e3 / len(by[dom]), "flops_per_launch": fl / len(by[dom]),
                     "share_of_step": tsum * 1e3 / sum(t for _, _, t in prof), "peak_source": src + " (sustained)"}

@@ -82,7 +82,7 @@ def test_tc_every_layer_vs_oracle_on_bf16_inputs(size, batch, workdir):
     for i, l in enumerate(layers):
         if l["type_name"] != "CONVOLUTIONAL":
             continue
-        is_tc = "conv_tc" in kinds.get(i, [])
+        is_tc = bool({"conv_tc", "conv_tc2"} & set(kinds.get(i, [])))
         # the stem reads the caller's f32 NCHW image directly (tensor-core stem: rounds it to bf16 on the fly)
         xin = (bf16_round(x) if is_tc else x) if i == 0 else got[i - 1]
         n_tc += is_tc

@@ -11,13 +11,14 @@ rows = list(csv.reader(open("gpurun_out/traffic_conv_tc.csv")))
 hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
 hdr = rows[hi]; mn, mu, mv, idc = hdr.index("Metric Name"), hdr.index("Metric Unit"), hdr.index("Metric Value"), hdr.index("ID")
 scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+kn = hdr.index("Kernel Name")
 tot, ids = 0.0, set()
 for r in rows[hi + 1:]:
-    if len(r) <= mv or not r[mn].startswith("dram__bytes"):
+    if len(r) <= mv or not r[mn].startswith("dram__bytes") or "k_conv_tc<2>" not in r[kn].replace("(int)2", "2"):
         continue
     tot += float(r[mv].replace(",", "")) * scale.get(r[mu], 1); ids.add(r[idc])
 out = {"yolov3-608-fp32-b16": {"dram_bytes_per_launch": tot / max(len(ids), 1), "launches": len(ids), "total_bytes": tot,
-                               "how": "ncu dram__bytes_read.sum + dram__bytes_write.sum over every k_conv_tc launch of one eager forward"}}
+                               "how": "ncu dram__bytes_read.sum + dram__bytes_write.sum over every k_conv_tc<2> launch (the dominant kernel) of one eager forward"}}
 json.dump(out, open("profiles/r01_traffic.json", "w"), indent=1)
 print(out)
 PY

@@ -63,6 +63,9 @@ struct TcParams {
     int xoff, yoff;
     int stages;
     uint32_t stage_bytes, a_bytes, b_bytes;   // per stage (all sub-blocks); per K-block A tile; per K-block B tile
+    int bstat;                                // 1: the whole filter matrix (nt == 1, <= 72 KB) is loaded once per CTA and stays in
+                                              //    shared memory; the ring then streams activations only
+    uint32_t bstat_bytes;
     int sps;                                  // K-blocks per pipeline stage (amortises the per-stage barrier round trip)
     uint32_t idesc, desc_hi;  // UMMA instruction descriptor; high word of the smem descriptors
     char *out; long out_ldc; int out_bf16; int n, n_store;
@@ -214,13 +217,15 @@ template <int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;   // 128B swizzle atoms are 1024B aligned
+    const uint32_t smemB = (smem_u32(smem_raw) + 1023u) & ~1023u;   // 128B swizzle atoms are 1024B aligned
+    const uint32_t smem0 = smemB + p.bstat_bytes;                   // [resident filter matrix][pipeline ring]
     const uint32_t bars = smem0 + (uint32_t)p.stages * p.stage_bytes;
     auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
     auto empty_bar = [&](int s) { return bars + 8u * (uint32_t)(p.stages + s); };
     auto tfull_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * p.stages + a); };
     auto tempty_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * p.stages + TC_ACC + a); };
-    const uint32_t tmem_slot = bars + 8u * (uint32_t)(2 * p.stages + 2 * TC_ACC);
+    const uint32_t bstat_bar = bars + 8u * (uint32_t)(2 * p.stages + 2 * TC_ACC);
+    const uint32_t tmem_slot = bstat_bar + 8u;
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
@@ -237,6 +242,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // tempty: one arrival per epilogue warp (of both CTAs when paired)
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < TC_ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), CG * TC_EPI_WARPS); }
+        mbar_init(bstat_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -275,6 +281,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const int xoff = p.xoff, yoff = p.yoff, stride2 = p.stride2, nt = p.nt, xt = p.xt;
             const uint32_t a_bytes = p.a_bytes, b_bytes = p.b_bytes, stage_bytes = p.stage_bytes;
             const uint32_t b_off = (uint32_t)sps * a_bytes;
+            const int bstat = p.bstat;
+            if (bstat) {   // resident filter matrix: kblocks boxes of [BN filters][BK], once
+                mbar_arrive_expect_tx(bstat_bar, p.bstat_bytes);
+                for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(smemB + (uint32_t)kb * b_bytes, &tmB, bstat_bar, kb * BK, 0);
+            }
             for (int w = w_first; w < p.num_work; w += w_step) {
                 const int n_idx = w % nt;
                 const int m = (CG == 2) ? 2 * (w / nt) + (int)rank : w / nt;
@@ -294,7 +305,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         continue;
                     }
                     // the leader's barrier collects the bytes of BOTH CTAs (the 2-CTA TMA form signals the leader)
-                    if (leader) mbar_arrive_expect_tx(fb, (uint32_t)(CG * nsub) * (a_bytes + b_bytes));
+                    if (leader) mbar_arrive_expect_tx(fb, (uint32_t)(CG * nsub) * (a_bytes + (bstat ? 0u : b_bytes)));
                     const long long ct0 = clock64();
                     for (int j = 0; j < nsub; ++j) {
                         const uint32_t ad = a_dst + (uint32_t)j * a_bytes, bd = b_dst + (uint32_t)j * b_bytes;
@@ -306,7 +317,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         } else {
                             if (stride2) tma_load_5d(ad, &tmA, fb, c0, kx & 1, x0 + (kx >> 1), ky & 1, J0 + (ky >> 1));
                             else tma_load_3d(ad, &tmA, fb, c0, x0 + kx + xoff, J0 + ky + yoff);
-                            tma_load_2d(bd, &tmB, fb, kcol, n0);
+                            if (!bstat) tma_load_2d(bd, &tmB, fb, kcol, n0);
                         }
                         kcol += BK;
                         if (++cb == cblocks) { cb = 0; if (++kx == fsize) { kx = 0; ++ky; } }
@@ -327,6 +338,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const uint32_t b_off = (uint32_t)sps * a_bytes;
             const uint64_t hi = (uint64_t)p.desc_hi << 32;
             long long w_full = 0, w_tempty = 0; const long long t_begin = clock64();
+            const int bstat = p.bstat;
+            if (bstat) { mbar_wait(bstat_bar, 0, 4); tc_fence_after(); }
             for (int w = w_first; w < p.num_work; w += w_step) {
                 { const long long c0 = clock64(); mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 1); w_tempty += clock64() - c0; }   // epilogue(s) drained this accumulator
                 tc_fence_after();
@@ -341,7 +354,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         // K-major operands; K advance of 16 bf16 = 32 bytes inside the swizzle row = +2 in the
                         // descriptor's 16-byte address units
                         uint64_t adesc = hi | (uint64_t)((((a_base + (uint32_t)j * a_bytes) & 0x3FFFFu) >> 4) | (1u << 16));
-                        uint64_t bdesc = hi | (uint64_t)((((b_base + (uint32_t)j * b_bytes) & 0x3FFFFu) >> 4) | (1u << 16));
+                        const uint32_t b_src = bstat ? smemB + (uint32_t)(kb0 + j) * b_bytes : b_base + (uint32_t)j * b_bytes;
+                        uint64_t bdesc = hi | (uint64_t)(((b_src & 0x3FFFFu) >> 4) | (1u << 16));
                         for (int k = 0; k < kk; ++k) {
                             if constexpr (CG == 2) umma2_bf16(d_tmem, adesc, bdesc, idesc, (uint32_t)((kb0 | j | k) != 0));
                             else if (kind != 0) umma_i8(d_tmem, adesc, bdesc, idesc, (uint32_t)((kb0 | j | k) != 0));
@@ -924,14 +938,22 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
     // several K-blocks per stage when they are small: the single MMA-issuing thread pays a fixed barrier round
     // trip per stage, which dominated the C<=64 layers (profiles/r01_notes.md)
     const uint32_t sps_target = getenv("YB_TC_SPS_TARGET") ? (uint32_t)atoi(getenv("YB_TC_SPS_TARGET")) : 64u * 1024u;
-    p.sps = (int)std::max<uint32_t>(1, std::min<uint32_t>(4, sps_target / (p.a_bytes + p.b_bytes)));
+    // small filter matrices stay resident in shared memory for the whole kernel (one TMA pass per CTA)
+    p.bstat = (p.cg == 1 && p.nt == 1 && (size_t)p.kblocks * p.b_bytes <= 72 * 1024 && !getenv("YB_TC_NO_BSTAT")) ? 1 : 0;
+    p.bstat_bytes = p.bstat ? (uint32_t)p.kblocks * p.b_bytes : 0u;
+    const uint32_t ring_blk = p.a_bytes + (p.bstat ? 0u : p.b_bytes);
+    p.sps = (int)std::max<uint32_t>(1, std::min<uint32_t>(4, sps_target / ring_blk));
     if (p.cg == 2) p.sps = 1;   // CTA pairs: 32 KB stages, 6 deep -- finer stages beat fewer barrier round trips here
     if (getenv("YB_TC_SPS")) p.sps = std::max(1, atoi(getenv("YB_TC_SPS")));
     if (getenv("YB_TC_SPS_CG2") && p.cg == 2) p.sps = std::max(1, atoi(getenv("YB_TC_SPS_CG2")));
     p.sps = std::min(p.sps, p.kblocks);
-    p.stage_bytes = (uint32_t)p.sps * (p.a_bytes + p.b_bytes);
+    {   // keep the ring at least 3 stages deep
+        const size_t avail = 192 * 1024 - p.bstat_bytes - sizeof(float) * (size_t)p.nt * BN;
+        while (p.sps > 1 && avail / ((size_t)p.sps * ring_blk) < 3) --p.sps;
+    }
+    p.stage_bytes = (uint32_t)p.sps * ring_blk;
     const size_t max_stages = getenv("YB_TC_MAX_STAGES") ? (size_t)atoi(getenv("YB_TC_MAX_STAGES")) : 8;
-    p.stages = (int)std::min<size_t>(max_stages, (192 * 1024 - sizeof(float) * (size_t)p.nt * BN) / p.stage_bytes);
+    p.stages = (int)std::min<size_t>(max_stages, (192 * 1024 - p.bstat_bytes - sizeof(float) * (size_t)p.nt * BN) / p.stage_bytes);
     if (p.stages < 2) fatal_throw("tc plan: tile does not fit shared memory");
     // UMMA instruction descriptor (kind::f16): D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TC_BM * p.cg) >> 4) << 24);
@@ -999,7 +1021,7 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
         cudaMalloc(&p.stats, sizeof(unsigned long long) * 8 * plan->grid);
         cudaMemset(p.stats, 0, sizeof(unsigned long long) * 8 * plan->grid);
     }
-    plan->smem = (size_t)p.stages * p.stage_bytes + 1024 /*alignment slack*/ + 8 * (2 * p.stages + 2 * TC_ACC) + 16 +
+    plan->smem = (size_t)p.stages * p.stage_bytes + p.bstat_bytes + 1024 /*alignment slack*/ + 8 * (2 * p.stages + 2 * TC_ACC + 1) + 16 +
                  sizeof(float) * (size_t)p.nt * BN /*bias*/ + 128 + 4096 * TC_EPI_WARPS /*epilogue staging*/;
     if (cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(k_conv_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
@@ -1076,6 +1098,8 @@ void tc_stem_launch(void *vp, const float *d_in_nchw, cudaStream_t s) {
     k_stem_tc<<<sp->grid, 128, 0, s>>>(p);
 }
 void tc_stem_free_plan(void *vp) { delete reinterpret_cast<StemPlan *>(vp); }
+
+int tc_plan_cta_group(void *vp) { return reinterpret_cast<TcPlan *>(vp)->p.cg; }
 
 void tc_launch(void *vp, cudaStream_t s) {
     TcPlan *plan = reinterpret_cast<TcPlan *>(vp);

@@ -30,8 +30,8 @@ namespace yb {
 const char *op_kind_name(int k) {
     static const char *names[] = {"input", "conv_simt", "conv_tc", "binarize", "conv_xnor", "quantize",
                                   "conv_int8", "maxpool", "upsample", "shortcut", "route_copy", "reorg",
-                                  "yolo", "region", "conv_tc_i8"};
-    return (k >= 0 && k < 15) ? names[k] : "?";
+                                  "yolo", "region", "conv_tc_i8", "conv_tc2"};
+    return (k >= 0 && k < 16) ? names[k] : "?";
 }
 
 enum { DT_F32 = 0, DT_BF16 = 1, DT_S8 = 2, DT_BITS = 3 };
@@ -559,7 +559,7 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                         tc_plan_fuse_yolo(plan, e->d_final[i + 1], net->layers[i + 1].classes);
                         yolo_fused[i + 1] = 1;
                     }
-                    e->ops.push_back(Op{OP_CONV_TC, i, [plan](cudaStream_t s) { tc_launch(plan, s); }});
+                    e->ops.push_back(Op{tc_plan_cta_group(plan) == 2 ? OP_CONV_TC2 : OP_CONV_TC, i, [plan](cudaStream_t s) { tc_launch(plan, s); }});
                 } else {
                     ConvP p{};
                     p.in = tin; p.out = tout; p.res = res;
