@@ -134,3 +134,56 @@ def test_bf16_network_vs_f32_oracle(name, workdir):
         e = np.concatenate([exp[b][i] for b in range(2)], 0).reshape(o.shape)
         err = util.rel_l2(o, e)
         assert err <= 3e-3, (name, i, err)
+
+
+def ksplitnet(h, w):
+    """Deep-K layers on small grids: every tensor-core layer has far fewer tiles than the GPU has SMs, so the whole
+    layer is one (tail) wave and the K-split schedule cuts each work item into several slices."""
+    c = cfgs._conv
+    return [cfgs._net(h, w),
+            c(32, 3),                   # 0 stem
+            c(256, 3, 2),               # 1 s2, K = 9*32
+            c(256, 3),                  # 2 CTA pairs (BN 256), K = 9*256: 36 stages
+            c(128, 1),                  # 3 1x1, K = 256
+            c(256, 3),                  # 4 + fused shortcut, K = 9*128
+            ("shortcut", {"from": "-3", "activation": "linear"}),   # 5
+            c(512, 3),                  # 6 two filter tiles of 256, CTA pairs
+            c(128, 3),                  # 7 BN 128 (single CTAs), K = 9*512: resident-B not possible
+            c(64, 3),                   # 8 BN 64, K = 9*128
+            c(255, 1, bn=False, act="linear"),   # 9 head (fused yolo), K = 64
+            cfgs._yolo("0,1,2", cfgs.COCO_ANCHORS, 9),
+            ("route", {"layers": "-4"}),                                # 11 -> layer 7
+            c(255, 3, bn=False, act="linear"),   # 12 f32 head with deep K (9*128), generic epilogue
+            cfgs._yolo("3,4,5", cfgs.COCO_ANCHORS, 9)]
+
+
+@pytest.mark.parametrize("h,w,batch", [(32, 32, 2), (64, 32, 3), (96, 96, 4)])
+def test_tc_ksplit_tail_matches_plain_schedule(h, w, batch, workdir):
+    """K-split tail wave (yb_conv_tc.cu): same numbers as the unsplit schedule up to f32 summation order, on every
+    layer, and the layers really are split."""
+    import yolo2_light_b200 as yb
+    cfg, wts = _files(workdir, f"ksplit{h}x{w}", ksplitnet(h, w), 31)
+    x = cfgs.synthetic_images(batch, 3, h, w, seed=9)
+    got = []
+    for ks in (0, 1):
+        net = yb.load_network(cfg, wts, batch=batch)
+        net.set_option("ksplit", ks)
+        net.set_option("fuse", 0)
+        for rep in range(3):     # flags must re-arm between launches
+            net.predict(x)
+        n_split = net.get_info("ksplit_layers")
+        assert net.get_info("tc_layers") >= 9
+        assert (n_split >= 3) if ks else (n_split == 0), n_split
+        got.append([net.fetch_layer(i) for i in range(net.n)])
+    for i, (a, b) in enumerate(zip(*got)):
+        # identical bf16 inputs per layer only if the previous layer agreed bit for bit; the drift of a few bf16 ulps
+        # accumulates down the (unfused, layer by layer) chain
+        assert util.rel_l2(b, a) <= 4e-3, (i, util.rel_l2(b, a))
+    # fused engine, CUDA graph replays
+    net = yb.load_network(cfg, wts, batch=batch)
+    ref = yb.load_network(cfg, wts, batch=batch)
+    ref.set_option("ksplit", 0)
+    for rep in range(3):
+        net.predict(x); ref.predict(x)
+    for i, o in net.detection_outputs().items():
+        assert util.rel_l2(o, ref.detection_outputs()[i]) <= 2e-3, i

@@ -21,7 +21,7 @@ from typing import List, Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libyolo2_light_b200.so")
+LIB_PATH = os.environ.get("YB_LIB") or os.path.join(_HERE, "libyolo2_light_b200.so")   # YB_LIB: A/B builds (development)
 
 YB_CONVOLUTIONAL, YB_MAXPOOL, YB_SOFTMAX, YB_ROUTE, YB_SHORTCUT = 0, 3, 4, 8, 13
 YB_REGION, YB_YOLO, YB_UPSAMPLE, YB_REORG, YB_BLANK = 21, 22, 23, 24, 25
@@ -88,6 +88,7 @@ def lib():
         "yb_network_set_device": (C.c_int, [vp, C.c_int]),
         "yb_network_set_precision": (C.c_int, [vp, C.c_int]),
         "yb_network_set_option": (C.c_int, [vp, C.c_char_p, C.c_int]),
+        "yb_network_get_info": (C.c_long, [vp, C.c_int, C.c_char_p]),
         "yb_network_predict": (fp, [vp, vp]),
         "yb_network_predict_quantized": (fp, [vp, vp]),
         "yb_network_predict_image_u8": (fp, [vp, vp, C.c_int, C.c_int, C.c_int]),
@@ -110,6 +111,8 @@ def lib():
         "yb_free_pinned": (None, [vp]),
     }
     for name, (res, args) in sig.items():
+        if "YB_LIB" in os.environ and not hasattr(L, name):
+            continue                 # an older A/B build may lack the newest entry points
         f = getattr(L, name)
         f.restype = res
         f.argtypes = args
@@ -123,7 +126,7 @@ EXPORTED_SYMBOLS = [
     "yb_fuse_conv_batchnorm", "yb_calculate_binary_weights", "yb_quantinization_and_get_multipliers",
     "yb_network_from_layers", "yb_free_network", "yb_network_num_layers", "yb_network_dims", "yb_network_layer",
     "yb_network_layer_outputs", "yb_network_input_calibration", "yb_set_batch_network", "yb_network_set_device",
-    "yb_network_set_precision", "yb_network_set_option", "yb_network_predict", "yb_network_predict_quantized",
+    "yb_network_set_precision", "yb_network_set_option", "yb_network_get_info", "yb_network_predict", "yb_network_predict_quantized",
     "yb_network_predict_image_u8", "yb_network_fetch_input", "yb_network_submit", "yb_network_collect", "yb_network_layer_output", "yb_network_forward_device", "yb_network_sync_outputs", "yb_network_fetch_layer",
     "yb_network_fetch_counts", "yb_forward_convolutional_layer", "yb_network_weight_arena",
     "yb_network_last_launches", "yb_network_profile", "yb_op_kind_name", "yb_get_network_boxes", "yb_alloc_pinned",
@@ -214,6 +217,9 @@ class Network:
 
     def set_option(self, name: str, value: int):
         _check(lib().yb_network_set_option(self._h, name.encode(), value) == 0)
+
+    def get_info(self, key: str, quantized: bool = False) -> int:
+        return int(lib().yb_network_get_info(self._h, int(quantized), key.encode()))
 
     # -- forward -------------------------------------------------------------------------------------
     def _out_shape(self, i: int):

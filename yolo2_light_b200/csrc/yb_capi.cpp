@@ -42,6 +42,7 @@ static Engine *get_engine(yb_network *n, int quantized, bool upload = true) {
         const char *nf = getenv("YB_NO_FUSE");
         opt.fuse = !(nf && nf[0] == '1') && net.fuse;
         opt.keep_counts = net.keep_counts;
+        opt.ksplit = net.ksplit;
         opt.q_index_offset = net.q_index_offset;
         net.engine[slot] = build_engine(&net, opt);
     }
@@ -209,9 +210,16 @@ int yb_network_set_option(yb_network *n, const char *name, int value) {
     if (!strcmp(name, "fuse")) net.fuse = value != 0;
     else if (!strcmp(name, "keep_counts")) net.keep_counts = value != 0;
     else if (!strcmp(name, "q_index_offset")) net.q_index_offset = value;
+    else if (!strcmp(name, "ksplit")) net.ksplit = value != 0;
     else { report(std::string("unknown option ") + name); return -1; }
     net.engine[0].reset(); net.engine[1].reset();
     return 0;
+}
+
+long yb_network_get_info(yb_network *n, int quantized, const char *key) {
+    YB_TRY
+    return engine_info(get_engine(n, quantized), key);
+    YB_CATCH(-1)
 }
 
 static float *predict_common(yb_network *n, const float *input, int quantized) {

@@ -67,6 +67,13 @@ struct TcParams {
                                               //    shared memory; the ring then streams activations only
     uint32_t bstat_bytes;
     int sps;                                  // K-blocks per pipeline stage (amortises the per-stage barrier round trip)
+    int kbs;                                  // pipeline stages per work item = ceil(kblocks / sps)
+    // K-split tail (wave quantisation): the last num_work % G work items ("tail") are cut along K into slices of sk_L
+    // stages, one slice per CTA (pair); a slice that does not end its work item dumps the raw f32 accumulator to
+    // sk_ws, the slice that does (the owner) adds those partials in its epilogue.  sk_T == 0: off.
+    int sk_T, sk_L;
+    float *sk_ws;                             // [grid][BN/4][128] float4
+    unsigned *sk_flags;                       // [grid][8 epilogue warps]: 1 = partial published (reset by its reader)
     uint32_t idesc, desc_hi;  // UMMA instruction descriptor; high word of the smem descriptors
     char *out; long out_ldc; int out_bf16; int n, n_store;
     const char *res; long res_ldc; int res_bf16;
@@ -163,6 +170,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+          "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+          "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -209,11 +227,59 @@ __device__ __forceinline__ void umma2_commit_both(uint32_t bar) {   // arrives o
                  ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
+// Work schedule of one CTA (CG=1) / CTA pair (CG=2), identical in every warp role: first this unit's slice of the
+// K-split tail (units of pipeline stages over the first sk_T work items), then whole work items round-robin.
+struct TcSched { int u, u_end, w_dp, w_step, num_work, kbs, lead0, lead1; };
+template <bool KS>
+__device__ __forceinline__ TcSched sched_init(const TcParams &p, int unit, int nunits) {
+    TcSched s;
+    s.kbs = p.kbs; s.num_work = p.num_work; s.w_step = nunits;
+    if constexpr (!KS) { s.u = s.u_end = s.lead0 = s.lead1 = 0; s.w_dp = unit; return s; }
+    const int U = p.sk_T * p.kbs;
+    s.u = min(unit * p.sk_L, U); s.u_end = min(s.u + p.sk_L, U);
+    s.w_dp = p.sk_T + unit;
+    // A slice whose last segment stops short of its work item's end only PUBLISHES a partial sum; it goes first, so
+    // that no partial ever waits behind a segment that itself waits for partials (which would chain the CTAs up).
+    s.lead0 = s.lead1 = 0;
+    if (s.u < s.u_end) {
+        const int wl = (s.u_end - 1) / s.kbs;
+        if (s.u_end < (wl + 1) * s.kbs) { s.lead0 = max(s.u, wl * s.kbs); s.lead1 = s.u_end; s.u_end = s.lead0; }
+    }
+    return s;
+}
+// next segment: work item w, stages [s0, s1) of its kbs stages
+template <bool KS>
+__device__ __forceinline__ bool sched_next(TcSched &s, int &w, int &s0, int &s1) {
+    if constexpr (!KS) {
+        if (s.w_dp >= s.num_work) return false;
+        w = s.w_dp; s.w_dp += s.w_step; s0 = 0; s1 = s.kbs;
+        return true;
+    }
+    if (s.lead0 < s.lead1) {
+        w = s.lead0 / s.kbs; s0 = s.lead0 - w * s.kbs; s1 = s.lead1 - w * s.kbs; s.lead1 = s.lead0;
+        return true;
+    }
+    if (s.u < s.u_end) {
+        w = s.u / s.kbs; s0 = s.u - w * s.kbs; s1 = min(s.kbs, s0 + (s.u_end - s.u)); s.u += s1 - s0;
+        return true;
+    }
+    if (s.w_dp >= s.num_work) return false;
+    w = s.w_dp; s.w_dp += s.w_step; s0 = 0; s1 = s.kbs;
+    return true;
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // CG = 1: one CTA per 128-pixel tile.  CG = 2: a CTA pair computes a 256-pixel x BN tile with cta_group::2 MMAs --
 // each CTA loads its own 128 pixels of A and HALF of the B (filter) tile, so the bytes every SM pulls through its
 // TMA unit per FLOP drop by a third; that unit (~64 B/clk/SM) is what bounds the BN=256 layers
 // (profiles/r01_notes.md).  The leader CTA (cluster rank 0) issues the MMAs for both.
-template <int CG>
+// KS: compiled with the K-split tail schedule (TcParams::sk_T); the KS = false instantiations carry none of its code.
+template <int CG, bool KS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -286,15 +352,20 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 mbar_arrive_expect_tx(bstat_bar, p.bstat_bytes);
                 for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(smemB + (uint32_t)kb * b_bytes, &tmB, bstat_bar, kb * BK, 0);
             }
-            for (int w = w_first; w < p.num_work; w += w_step) {
+            TcSched sch = sched_init<KS>(p, w_first, w_step);
+            int w, seg0, seg1;
+            while (sched_next<KS>(sch, w, seg0, seg1)) {
                 const int n_idx = w % nt;
                 const int m = (CG == 2) ? 2 * (w / nt) + (int)rank : w / nt;
                 const int x0 = (m % xt) * p.TW;
                 const int J0 = (m / xt) * p.TH;
                 const int n0 = n_idx * p.BN + (int)rank * (p.BN / CG);
-                int cb = 0, kx = 0, ky = 0, kcol = 0;   // channel block, tap x/y, K column of the weight matrix
-                for (int kb0 = 0; kb0 < kblocks; kb0 += sps) {
-                    const int nsub = min(sps, kblocks - kb0);
+                const int kb_begin = seg0 * sps, kb_end = min(kblocks, seg1 * sps);
+                // channel block, tap x/y, K column of the weight matrix at the first K-block of the segment
+                const int tap0 = kb_begin / cblocks;
+                int cb = kb_begin - tap0 * cblocks, ky = tap0 / fsize, kx = tap0 - (tap0 / fsize) * fsize, kcol = kb_begin * BK;
+                for (int kb0 = kb_begin; kb0 < kb_end; kb0 += sps) {
+                    const int nsub = min(sps, kb_end - kb0);
                     { const long long c0 = clock64(); mbar_wait(empty_bar(stage), phase ^ 1u, 0); w_empty += clock64() - c0; }
                     const uint32_t fb = full_bar(stage);
                     const uint32_t a_dst = smem0 + (uint32_t)stage * stage_bytes;
@@ -340,12 +411,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             long long w_full = 0, w_tempty = 0; const long long t_begin = clock64();
             const int bstat = p.bstat;
             if (bstat) { mbar_wait(bstat_bar, 0, 4); tc_fence_after(); }
-            for (int w = w_first; w < p.num_work; w += w_step) {
+            TcSched sch = sched_init<KS>(p, w_first, w_step);
+            int w, seg0, seg1;
+            while (sched_next<KS>(sch, w, seg0, seg1)) {
                 { const long long c0 = clock64(); mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 1); w_tempty += clock64() - c0; }   // epilogue(s) drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                for (int kb0 = 0; kb0 < kblocks; kb0 += sps) {
-                    const int nsub = min(sps, kblocks - kb0);
+                const int kb_begin = seg0 * sps, kb_end = min(kblocks, seg1 * sps);
+                for (int kb0 = kb_begin; kb0 < kb_end; kb0 += sps) {
+                    const int nsub = min(sps, kb_end - kb0);
                     { const long long c0 = clock64(); mbar_wait(full_bar(stage), phase, 2); w_full += clock64() - c0; }   // TMA bytes have landed
                     tc_fence_after();
                     const uint32_t a_base = smem0 + (uint32_t)stage * stage_bytes;
@@ -356,10 +430,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         uint64_t adesc = hi | (uint64_t)((((a_base + (uint32_t)j * a_bytes) & 0x3FFFFu) >> 4) | (1u << 16));
                         const uint32_t b_src = bstat ? smemB + (uint32_t)(kb0 + j) * b_bytes : b_base + (uint32_t)j * b_bytes;
                         uint64_t bdesc = hi | (uint64_t)(((b_src & 0x3FFFFu) >> 4) | (1u << 16));
+                        const int first = (kb0 - kb_begin) | j;     // 0 on the first K-block of the segment: overwrite the accumulator
                         for (int k = 0; k < kk; ++k) {
-                            if constexpr (CG == 2) umma2_bf16(d_tmem, adesc, bdesc, idesc, (uint32_t)((kb0 | j | k) != 0));
-                            else if (kind != 0) umma_i8(d_tmem, adesc, bdesc, idesc, (uint32_t)((kb0 | j | k) != 0));
-                            else umma_bf16(d_tmem, adesc, bdesc, idesc, (uint32_t)((kb0 | j | k) != 0));
+                            if constexpr (CG == 2) umma2_bf16(d_tmem, adesc, bdesc, idesc, (uint32_t)((first | k) != 0));
+                            else if (kind != 0) umma_i8(d_tmem, adesc, bdesc, idesc, (uint32_t)((first | k) != 0));
+                            else umma_bf16(d_tmem, adesc, bdesc, idesc, (uint32_t)((first | k) != 0));
                             adesc += 2; bdesc += 2;
                         }
                     }
@@ -388,7 +463,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const bool leaky = p.act == ACT_LEAKY, leaky2 = p.act2 == ACT_LEAKY;
         int acc = 0; uint32_t acc_phase = 0;
         long long w_tfull = 0; const long long t_begin = clock64();
-        for (int w = w_first; w < p.num_work; w += w_step) {
+        TcSched sch = sched_init<KS>(p, w_first, w_step);
+        int w, seg0, seg1;
+        while (sched_next<KS>(sch, w, seg0, seg1)) {
+            // K-split tail: a segment that stops short of the work item's last stage only publishes its raw accumulator;
+            // the segment that ends the work item adds the npart partials of the CTAs (pairs) gA .. unit-1 before it
+            const bool seg_partial = KS && seg1 < p.kbs;
+            const int npart = (KS && seg0 > 0 && !seg_partial) ? w_first - (w * p.kbs) / p.sk_L : 0;
             const int n_idx = w % p.nt;
             const int m = (CG == 2) ? 2 * (w / p.nt) + (int)rank : w / p.nt;
             const int ox = (m % p.xt) * p.TW + tx;
@@ -421,6 +502,82 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             { const long long c0 = clock64(); mbar_wait(tfull_bar(acc), acc_phase, 3); w_tfull += clock64() - c0; }
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+
+            if constexpr (KS) {
+                auto flag_of = [&](int unit) { return p.sk_flags + ((size_t)(unit * CG + (int)rank) * TC_EPI_WARPS + (warp - 2)); };
+                auto ws_of = [&](int unit) { return reinterpret_cast<float4 *>(p.sk_ws) + (size_t)(unit * CG + (int)rank) * (size_t)(TC_BM * 64); };
+                if (seg_partial) {
+                    // publish the raw f32 accumulator ([column/4][row] float4: a warp store is 512 contiguous bytes)
+                    float4 *dst = ws_of(w_first);
+                    for (int f0 = cbeg; f0 < cend; f0 += 32) {
+                        uint32_t v0[32];
+                        tmem_ld32(taddr + (uint32_t)f0, v0);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int g4 = 0; g4 < 8; ++g4)
+                            __stcg(dst + (size_t)((f0 >> 2) + g4) * TC_BM + r,
+                                   make_float4(__uint_as_float(v0[g4 * 4]), __uint_as_float(v0[g4 * 4 + 1]),
+                                               __uint_as_float(v0[g4 * 4 + 2]), __uint_as_float(v0[g4 * 4 + 3])));
+                    }
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) st_release_u32(flag_of(w_first), 1u);
+                } else if (npart) {
+                    // owner: fold the partial sums of CTAs (pairs) gA .. unit-1 into the TMEM accumulator, then run the
+                    // ordinary epilogue below on it
+                    const int gA = w_first - npart;
+                    for (int pc = 0; pc < npart; ++pc) {
+                        const unsigned *fl = flag_of(gA + pc);
+                        if (ld_acquire_u32(fl) == 0u) {
+                            const long long t0 = clock64();
+                            while (ld_acquire_u32(fl) == 0u) {
+                                if (clock64() - t0 > 4000000000LL) { printf("yb k_conv_tc: K-split partial timeout (block %d warp %d)\n", blockIdx.x, warp); __trap(); }
+                            }
+                        }
+                    }
+                    // 16 float4 loads in flight per thread: the fold is a latency-bound L2 read (profiles/r01_notes.md)
+                    auto add4 = [](uint32_t (&v)[32], int g4, const float4 &t) {
+                        v[g4 * 4 + 0] = __float_as_uint(__uint_as_float(v[g4 * 4 + 0]) + t.x);
+                        v[g4 * 4 + 1] = __float_as_uint(__uint_as_float(v[g4 * 4 + 1]) + t.y);
+                        v[g4 * 4 + 2] = __float_as_uint(__uint_as_float(v[g4 * 4 + 2]) + t.z);
+                        v[g4 * 4 + 3] = __float_as_uint(__uint_as_float(v[g4 * 4 + 3]) + t.w);
+                    };
+                    for (int f0 = cbeg; f0 < cend; f0 += 64) {
+                        if (cend - f0 >= 64) {
+                            uint32_t v0[32], v1[32];
+                            tmem_ld32(taddr + (uint32_t)f0, v0);
+                            tmem_ld32(taddr + (uint32_t)f0 + 32u, v1);
+                            for (int pc = 0; pc < npart; ++pc) {
+                                const float4 *src = ws_of(gA + pc) + (size_t)(f0 >> 2) * TC_BM + r;
+                                float4 t[16];
+#pragma unroll
+                                for (int g4 = 0; g4 < 16; ++g4) t[g4] = __ldcg(src + (size_t)g4 * TC_BM);
+                                if (pc == 0) tmem_ld_wait();
+#pragma unroll
+                                for (int g4 = 0; g4 < 8; ++g4) { add4(v0, g4, t[g4]); add4(v1, g4, t[8 + g4]); }
+                            }
+                            tmem_st32(taddr + (uint32_t)f0, v0);
+                            tmem_st32(taddr + (uint32_t)f0 + 32u, v1);
+                        } else {
+                            uint32_t v[32];
+                            tmem_ld32(taddr + (uint32_t)f0, v);
+                            tmem_ld_wait();
+                            for (int pc = 0; pc < npart; ++pc) {
+                                const float4 *src = ws_of(gA + pc) + (size_t)(f0 >> 2) * TC_BM + r;
+                                float4 t[8];
+#pragma unroll
+                                for (int g4 = 0; g4 < 8; ++g4) t[g4] = __ldcg(src + (size_t)g4 * TC_BM);
+#pragma unroll
+                                for (int g4 = 0; g4 < 8; ++g4) add4(v, g4, t[g4]);
+                            }
+                            tmem_st32(taddr + (uint32_t)f0, v);
+                        }
+                    }
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) for (int pc = 0; pc < npart; ++pc) *flag_of(gA + pc) = 0u;   // re-arm for the next launch
+                }
+            }
 
             auto finish = [&](const uint32_t (&v)[32], const uint4 (&rr)[4], int f0) {
                 if (!valid || (n0 + f0) >= p.n_store) return;
@@ -483,6 +640,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 }
             };
 
+            if (seg_partial) {
+                // accumulator already published above
+            } else
             if (p.kind == 2) {
                 // ---- XNOR as +-1 int8: acc == 2*count - K (exact); out = act((float)acc * mean + bias) in the reference's
                 // float op order (additionally.c:1531, yolov2_forward_network.c:243-261)
@@ -708,7 +868,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     uint32_t v0[32];
                     tmem_ld32(taddr + (uint32_t)f0, v0);
                     tmem_ld_wait();
-                    finish(v0, rv[0], f0);
+                        finish(v0, rv[0], f0);
                 }
             }
             tc_fence_before();
@@ -952,6 +1112,8 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
         while (p.sps > 1 && avail / ((size_t)p.sps * ring_blk) < 3) --p.sps;
     }
     p.stage_bytes = (uint32_t)p.sps * ring_blk;
+    p.kbs = (p.kblocks + p.sps - 1) / p.sps;
+    p.sk_T = 0; p.sk_L = 1;
     const size_t max_stages = getenv("YB_TC_MAX_STAGES") ? (size_t)atoi(getenv("YB_TC_MAX_STAGES")) : 8;
     p.stages = (int)std::min<size_t>(max_stages, (192 * 1024 - p.bstat_bytes - sizeof(float) * (size_t)p.nt * BN) / p.stage_bytes);
     if (p.stages < 2) fatal_throw("tc plan: tile does not fit shared memory");
@@ -1023,8 +1185,10 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
     }
     plan->smem = (size_t)p.stages * p.stage_bytes + p.bstat_bytes + 1024 /*alignment slack*/ + 8 * (2 * p.stages + 2 * TC_ACC + 1) + 16 +
                  sizeof(float) * (size_t)p.nt * BN /*bias*/ + 128 + 4096 * TC_EPI_WARPS /*epilogue staging*/;
-    if (cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(k_conv_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(k_conv_tc<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_conv_tc<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_conv_tc<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_conv_tc<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
         fatal_throw("cudaFuncSetAttribute(k_conv_tc) failed");
     return plan;
 }
@@ -1068,6 +1232,45 @@ void *tc_make_plan_xnor(const Layer &l, const TV &q, const TV &out, const void *
     plan->p.mean = d_mean;
     plan->p.xK = l.size * l.size * l.c;
     return plan;
+}
+
+// K-split of the tail wave (see TcParams::sk_T).  With G CTAs (pairs) and num_work = R*G + T work items, the plain
+// schedule costs R+1 waves; cutting the T tail items along K into G equal slices costs R + L/kbs waves plus the
+// partial-sum round trip through L2 (hidden behind the next work item's main loop when R > 0).
+// `ws`: sms * 128 KB, `flags`: sms * 8 words, zero-initialised, owned by the caller (one per stream of execution).
+size_t tc_ksplit_ws_bytes(int sms) { return (size_t)sms * TC_BM * 256 * sizeof(float); }
+size_t tc_ksplit_flag_bytes(int sms) { return (size_t)sms * TC_EPI_WARPS * sizeof(unsigned); }
+int tc_plan_enable_ksplit(void *vp, float *ws, unsigned *flags) {
+    TcPlan *plan = reinterpret_cast<TcPlan *>(vp);
+    TcParams &p = plan->p;
+    const char *ev = getenv("YB_TC_KSPLIT");
+    if (ev && ev[0] == '0') return 0;
+    if (p.kind != 0 || !ws || !flags) return 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int G = sms / p.cg;
+    const int R = p.num_work / G, T = p.num_work % G;
+    if (T == 0) return 0;
+    // Only deep-K layers: with few stages per work item the epilogue, not the tensor pipe, bounds the tile, and the
+    // partial-sum round trip (one more accumulator read + ~2 us of L2 latency per partial) costs more than the wave saves.
+    const int mink = getenv("YB_TC_KSPLIT_MINK") ? atoi(getenv("YB_TC_KSPLIT_MINK")) : 16;
+    if (p.kbs < mink) return 0;
+    const int pmax = getenv("YB_TC_KSPLIT_PIECES") ? std::max(1, atoi(getenv("YB_TC_KSPLIT_PIECES"))) : 3;
+    const int lmin = std::max(2, (p.kbs + pmax - 1) / pmax);           // at most ~pmax slices per work item
+    int L = std::max(lmin, (T * p.kbs + G - 1) / G);
+    if (L >= p.kbs) return 0;
+    // stage-times: exposed cost of the partial round trip (hidden behind the next item unless this is the only wave)
+    // Predicted gain in stage-times.  The partial round trip costs ~6 stages, and the idle tail of the plain schedule is
+    // not all waste: the next kernel's prologue runs in it (programmatic dependent launch).  Measured on yolov3-608
+    // (profiles/r01_notes.md): layers below ~12 % predicted gain came out slower, the 19x19 3x3 layers 5-10 % faster.
+    const double ovh = (R == 0) ? 10.0 : 6.0;
+    const double before = (double)(R + 1) * p.kbs, after = (double)R * p.kbs + L + ovh;
+    const double mingain = getenv("YB_TC_KSPLIT_MINGAIN") ? atof(getenv("YB_TC_KSPLIT_MINGAIN")) : 0.12;
+    if (before - after < mingain * before) return 0;
+    p.sk_T = T; p.sk_L = L; p.sk_ws = ws; p.sk_flags = flags;
+    plan->grid = p.cg * G;
+    return 1;
 }
 
 struct StemPlan { StemTcP p; int grid; };
@@ -1119,8 +1322,15 @@ void tc_launch(void *vp, cudaStream_t s) {
         ++na;
     }
     cfg.attrs = attr; cfg.numAttrs = na;
-    if (plan->p.cg == 2) cudaLaunchKernelEx(&cfg, k_conv_tc<2>, plan->tmA, plan->tmB, plan->p);
-    else cudaLaunchKernelEx(&cfg, k_conv_tc<1>, plan->tmA, plan->tmB, plan->p);
+    static const bool ks_always = getenv("YB_TC_KS_ALWAYS") != nullptr;   // experiment: one kernel variant for every layer
+    const bool ks = plan->p.sk_T > 0 || ks_always;
+    if (plan->p.cg == 2) {
+        if (ks) cudaLaunchKernelEx(&cfg, k_conv_tc<2, true>, plan->tmA, plan->tmB, plan->p);
+        else cudaLaunchKernelEx(&cfg, k_conv_tc<2, false>, plan->tmA, plan->tmB, plan->p);
+    } else {
+        if (ks) cudaLaunchKernelEx(&cfg, k_conv_tc<1, true>, plan->tmA, plan->tmB, plan->p);
+        else cudaLaunchKernelEx(&cfg, k_conv_tc<1, false>, plan->tmA, plan->tmB, plan->p);
+    }
 }
 
 void tc_free_plan(void *vp) {
@@ -1131,9 +1341,9 @@ void tc_free_plan(void *vp) {
         cudaMemcpy(h.data(), plan->p.stats, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
         double m[8] = {0};
         for (int b = 0; b < plan->grid; ++b) for (int k = 0; k < 8; ++k) m[k] += (double)h[8 * b + k] / plan->grid;
-        fprintf(stderr, "TCSTATS %-28s cg %d tiles/cta %.1f kb %d sps %d BN %d | producer: wait_empty %.0f tma_issue %.0f total %.0f | mma: wait_full %.0f "
+        fprintf(stderr, "TCSTATS %-28s cg %d tiles/cta %.1f kb %d sps %d BN %d ksplit T%d L%d/%d | producer: wait_empty %.0f tma_issue %.0f total %.0f | mma: wait_full %.0f "
                         "wait_tempty %.0f total %.0f | epi: wait_tfull %.0f total %.0f\n", plan->desc, plan->p.cg,
-                (double)plan->p.num_tiles / plan->grid * 1.0, plan->p.kblocks, plan->p.sps, plan->p.BN, m[0], m[7], m[1], m[2], m[3], m[4], m[5], m[6]);
+                (double)plan->p.num_tiles / plan->grid * 1.0, plan->p.kblocks, plan->p.sps, plan->p.BN, plan->p.sk_T, plan->p.sk_L, plan->p.kbs, m[0], m[7], m[1], m[2], m[3], m[4], m[5], m[6]);
         cudaFree(plan->p.stats);
     }
     delete plan;

@@ -22,6 +22,12 @@ void *tc_make_plan_xnor(const Layer &l, const TV &q, const TV &out, const void *
                         const float *d_mean, int *counts_out);
 // fuse the following [yolo] layer into the (f32-output) plan: logistic + NCHW store in the epilogue
 void tc_plan_fuse_yolo(void *plan, float *d_yolo_nchw, int classes);
+// K-split of the tail wave of a bf16 plan (wave quantisation): `ws` (tc_ksplit_ws_bytes) and `flags`
+// (tc_ksplit_flag_bytes, zeroed) belong to the caller and may be shared by all plans that run on one stream.
+// Returns 1 if the plan's schedule was changed.
+size_t tc_ksplit_ws_bytes(int sms);
+size_t tc_ksplit_flag_bytes(int sms);
+int tc_plan_enable_ksplit(void *plan, float *ws, unsigned *flags);
 // tensor-core stem (3-channel 3x3 from the caller's NCHW f32 image, bf16 NHWC out)
 int tc_stem_supported(const Layer &l, const TV &out);
 void *tc_stem_make_plan(const Layer &l, const TV &out, const void *d_w_32x32_bf16, const float *d_bias);

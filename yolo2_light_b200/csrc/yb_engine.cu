@@ -72,6 +72,8 @@ struct Engine {
     cudaGraphExec_t graph_exec = nullptr;
     bool graph_failed = false;
     std::vector<void *> tc_plans;      // opaque per-layer state of the tensor-core path (tensor maps)
+    int n_tc = 0, n_ksplit = 0;
+    float *ksplit_ws = nullptr; unsigned *ksplit_flags = nullptr;   // partial sums / flags of the K-split tail (yb_conv_tc.cu)
     std::function<void(const float *, cudaStream_t)> first_op;   // consumes the caller's NCHW images (pointer varies per call)
     int first_kind = OP_INPUT, first_layer = -1;
     void *stem_plan = nullptr;
@@ -97,6 +99,8 @@ Engine::~Engine() {
     for (int32_t *p : d_counts) if (p) cudaFree(p);
     for (void *p : tc_plans) tc_free_plan(p);
     if (stem_plan) tc_stem_free_plan(stem_plan);
+    if (ksplit_ws) cudaFree(ksplit_ws);
+    if (ksplit_flags) cudaFree(ksplit_flags);
     if (d_u8) cudaFree(d_u8);
     for (Slot &sl : slots) {
         if (sl.d_in) cudaFree(sl.d_in);
@@ -554,6 +558,15 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                                               e->w_arena + cw[i].w_bf16, cw[i].ldn,
                                               reinterpret_cast<const float *>(e->w_arena + cw[i].bias));
                     e->tc_plans.push_back(plan);
+                    if (!e->ksplit_ws) {
+                        int sms = 148;
+                        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, opt.device);
+                        CUDA_OK(cudaMalloc(&e->ksplit_ws, tc_ksplit_ws_bytes(sms)));
+                        CUDA_OK(cudaMalloc(&e->ksplit_flags, tc_ksplit_flag_bytes(sms)));
+                        CUDA_OK(cudaMemset(e->ksplit_flags, 0, tc_ksplit_flag_bytes(sms)));
+                    }
+                    ++e->n_tc;
+                    if (opt.ksplit) e->n_ksplit += tc_plan_enable_ksplit(plan, e->ksplit_ws, e->ksplit_flags);
                     if (opt.fuse && fused_into[i] < 0 && odt == DT_F32 && i + 1 < nl && net->layers[i + 1].type == YB_YOLO &&
                         cons[i].size() == 1 && cons[i][0] == i + 1 && e->d_final[i + 1] && !getenv("YB_NO_YOLO_FUSE")) {
                         tc_plan_fuse_yolo(plan, e->d_final[i + 1], net->layers[i + 1].classes);
@@ -996,6 +1009,12 @@ int engine_fetch_counts(Engine *e, int layer, int32_t *dst, size_t count) {
 
 void engine_weight_arena(Engine *e, void **ptr, size_t *bytes) { *ptr = e->w_arena; *bytes = e->w_bytes; }
 int engine_num_launches(Engine *e) { return (int)e->ops.size(); }
+long engine_info(Engine *e, const char *key) {
+    if (!strcmp(key, "launches")) return (long)e->ops.size();
+    if (!strcmp(key, "tc_layers")) return e->n_tc;
+    if (!strcmp(key, "ksplit_layers")) return e->n_ksplit;
+    return -1;
+}
 
 int engine_profile(Engine *e, const void *d_input, int *layer_idx, int *op_kind, float *ms, int max) {
     CUDA_OK(cudaSetDevice(e->opt.device));

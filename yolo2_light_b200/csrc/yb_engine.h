@@ -26,6 +26,7 @@ struct EngineOptions {
     bool upload = true;        // upload the weight arena (false on non-root ranks before the broadcast)
     int q_index_offset = 0;    // added to the layer index in the `i >= 1` INT8 rule (single-layer runs)
     bool keep_counts = false;  // keep raw XNOR popcounts / INT8 accumulators (tests)
+    bool ksplit = true;        // K-split of the tail wave of the tensor-core convolutions
 };
 
 struct Engine;
@@ -42,6 +43,7 @@ void engine_fetch_input(Engine *e, float *dst);
 int engine_fetch_counts(Engine *e, int layer, int32_t *dst, size_t count);
 void engine_weight_arena(Engine *e, void **ptr, size_t *bytes);
 int engine_num_launches(Engine *e);
+long engine_info(Engine *e, const char *key);   // "launches", "tc_layers", "ksplit_layers"; -1 unknown
 int engine_profile(Engine *e, const void *d_input, int *layer_idx, int *op_kind, float *ms, int max);
 void *engine_stream(Engine *e);
 const char *op_kind_name(int k);

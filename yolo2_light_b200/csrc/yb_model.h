@@ -49,6 +49,7 @@ struct Network {
     int last_launches = 0;
     bool fuse = true;          // conv+shortcut fusion / route aliasing (diagnostic switch)
     bool keep_counts = false;  // keep raw XNOR popcounts / INT8 accumulators (tests)
+    bool ksplit = true;        // K-split tail wave of the tensor-core convolutions (yb_conv_tc.cu)
     int q_index_offset = 0;    // see EngineOptions
 };
 
