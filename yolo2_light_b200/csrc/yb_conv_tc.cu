@@ -323,8 +323,17 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // bias (folded batch-norm) for all filter tiles -> shared memory, once per CTA
     float *bias_s = reinterpret_cast<float *>(smem_raw + (tmem_slot + 16u - smem_u32(smem_raw)));
     // 4 KB of staging per epilogue warp (32 rows x 128 B, XOR-swizzled) for the coalescing transposes
-    const uint32_t stg_base = ((tmem_slot + 16u + 4u * (uint32_t)(p.nt * p.BN)) + 127u) & ~127u;
+    // fused [yolo]: one bit per filter, set where the entry is a box width/height (no logistic)
+    uint32_t *ymask_s = reinterpret_cast<uint32_t *>(bias_s + p.nt * p.BN);
+    const uint32_t stg_base = ((tmem_slot + 16u + 4u * (uint32_t)(p.nt * p.BN) + (uint32_t)(p.nt * p.BN / 8)) + 127u) & ~127u;
     for (int i = threadIdx.x; i < p.nt * p.BN; i += TC_THREADS) bias_s[i] = (i < p.n) ? __ldg(p.bias + i) : 0.f;
+    if (p.yolo_out) {
+        for (int wd = threadIdx.x; wd < p.nt * p.BN / 32; wd += TC_THREADS) {
+            uint32_t m = 0;
+            for (int j = 0; j < 32; ++j) { const int e = (wd * 32 + j) % p.yolo_per; if (e == 2 || e == 3) m |= 1u << j; }
+            ymask_s[wd] = m;
+        }
+    }
     tc_fence_before();
     if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
@@ -618,17 +627,16 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     // detection head with the [yolo] layer fused: logistic on x, y, objectness and class entries (w, h stay
                     // raw), written straight into the NCHW tensor the reference decoder reads -- the f32 NHWC copy of the
                     // head and the separate yolo kernel disappear
-                    int e = (n0 + f0) % p.yolo_per;
-                    float *dst = p.yolo_out + (((size_t)img * p.n + (n0 + f0)) * p.OH + oy) * (size_t)p.OW + ox;
+                    const int c0 = n0 + f0;
+                    const int nvalid = p.n - c0;                       // columns >= n are padding
+                    const uint32_t raw = ymask_s[c0 >> 5];             // bit j: entry (c0 + j) % (4+classes+1) is w or h -> stays raw
+                    float *dst = p.yolo_out + (((size_t)img * p.n + c0) * p.OH + oy) * (size_t)p.OW + ox;
                     const size_t plane = (size_t)p.OH * p.OW;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        if (n0 + f0 + j < p.n) {
-                            float v = x[j];
-                            if (e != 2 && e != 3) v = 1.f / (1.f + __expf(-v));
-                            dst[(size_t)j * plane] = v;
-                        }
-                        if (++e == p.yolo_per) e = 0;
+                        const float sg = __fdividef(1.f, 1.f + __expf(-x[j]));
+                        const float v = ((raw >> j) & 1u) ? x[j] : sg;
+                        if (j < nvalid) dst[(size_t)j * plane] = v;
                     }
                 } else {
                     float4 *op = reinterpret_cast<float4 *>(orow + (size_t)(n0 + f0) * 4);
@@ -1057,7 +1065,7 @@ int tc_conv_supported(const Layer &l, const TV &in, const TV &out, bool out_bf16
 
 static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &out, bool out_bf16, const TV &res,
                               bool res_bf16, int act2, const void *d_weights_bf16, int ldn, const float *d_bias,
-                              float alpha1, int *acc_out) {
+                              float alpha1, int *acc_out, int wide_rows = 0) {
     TcPlan *plan = new TcPlan();
     memset(plan, 0, sizeof(*plan));
     TcParams &p = plan->p;
@@ -1082,6 +1090,15 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
         const int th = 128 / tw;
         const double cost = (double)((p.OW + tw - 1) / tw) * tw * (double)((rows + th - 1) / th) * th;
         if (cost < best - 0.5) { best = cost; bestTW = tw; }
+    }
+    if (wide_rows) {
+        // the epilogue will scatter NCHW planes (fused [yolo]): a warp's 32 accumulator rows should be as few image-row
+        // runs as possible, so take the widest tile whose padded work stays within 30 % of the minimum
+        for (int tw = 64; tw > bestTW; tw /= 2) {
+            const int th = 128 / tw;
+            const double cost = (double)((p.OW + tw - 1) / tw) * tw * (double)((rows + th - 1) / th) * th;
+            if (cost <= 1.3 * best) { bestTW = tw; break; }
+        }
     }
     p.TW = bestTW; p.TH = 128 / bestTW;
     p.TWlog2 = 0; while ((1 << p.TWlog2) < p.TW) ++p.TWlog2;
@@ -1184,7 +1201,7 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
         cudaMemset(p.stats, 0, sizeof(unsigned long long) * 8 * plan->grid);
     }
     plan->smem = (size_t)p.stages * p.stage_bytes + p.bstat_bytes + 1024 /*alignment slack*/ + 8 * (2 * p.stages + 2 * TC_ACC + 1) + 16 +
-                 sizeof(float) * (size_t)p.nt * BN /*bias*/ + 128 + 4096 * TC_EPI_WARPS /*epilogue staging*/;
+                 sizeof(float) * (size_t)p.nt * BN /*bias*/ + (size_t)p.nt * BN / 8 /*yolo mask*/ + 128 + 4096 * TC_EPI_WARPS /*epilogue staging*/;
     if (cudaFuncSetAttribute(k_conv_tc<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(k_conv_tc<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(k_conv_tc<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
@@ -1194,8 +1211,8 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
 }
 
 void *tc_make_plan(const Layer &l, const TV &in, const TV &out, bool out_bf16, const TV &res, bool res_bf16,
-                   int act2, const void *d_weights_bf16, int ldn, const float *d_bias) {
-    return make_plan_common(0, l, in, out, out_bf16, res, res_bf16, act2, d_weights_bf16, ldn, d_bias, 0.f, nullptr);
+                   int act2, const void *d_weights_bf16, int ldn, const float *d_bias, int wide_rows) {
+    return make_plan_common(0, l, in, out, out_bf16, res, res_bf16, act2, d_weights_bf16, ldn, d_bias, 0.f, nullptr, wide_rows);
 }
 
 // INT8 variant (reference forward_convolutional_layer_q, yolov2_forward_network_quantized.c:527-631) on

@@ -10,9 +10,10 @@ namespace yb {
 
 // non-zero if the bf16 tcgen05 kernel takes this layer (input view `in`, bf16 or f32 output)
 int tc_conv_supported(const Layer &l, const TV &in, const TV &out, bool out_bf16);
-// builds the per-layer launch state (TMA tensor maps, tile schedule); throws yb::Error on failure
+// builds the per-layer launch state (TMA tensor maps, tile schedule); throws yb::Error on failure.
+// wide_rows: prefer wide pixel tiles (the plan will get tc_plan_fuse_yolo: NCHW plane stores in the epilogue)
 void *tc_make_plan(const Layer &l, const TV &in, const TV &out, bool out_bf16, const TV &res, bool res_bf16,
-                   int act2, const void *d_weights_bf16, int ldn, const float *d_bias);
+                   int act2, const void *d_weights_bf16, int ldn, const float *d_bias, int wide_rows = 0);
 // INT8 (kind::i8) variant
 int tc_i8_supported(const Layer &l, const TV &q, const TV &out);
 void *tc_make_plan_i8(const Layer &l, const TV &q, const TV &out, const void *d_weights_s8, int ldn, const float *d_bias,

@@ -554,9 +554,12 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                     if (!res.base) fatal_throw("engine: shortcut source not placed");
                 }
                 if (use_tc[i]) {
+                    const bool fuse_yolo = opt.fuse && fused_into[i] < 0 && odt == DT_F32 && i + 1 < nl &&
+                                           net->layers[i + 1].type == YB_YOLO && cons[i].size() == 1 && cons[i][0] == i + 1 &&
+                                           e->d_final[i + 1] && !getenv("YB_NO_YOLO_FUSE");
                     void *plan = tc_make_plan(l, tin, tout, odt == DT_BF16, res, rdt == DT_BF16, act2,
                                               e->w_arena + cw[i].w_bf16, cw[i].ldn,
-                                              reinterpret_cast<const float *>(e->w_arena + cw[i].bias));
+                                              reinterpret_cast<const float *>(e->w_arena + cw[i].bias), fuse_yolo ? 1 : 0);
                     e->tc_plans.push_back(plan);
                     if (!e->ksplit_ws) {
                         int sms = 148;
@@ -567,8 +570,7 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                     }
                     ++e->n_tc;
                     if (opt.ksplit) e->n_ksplit += tc_plan_enable_ksplit(plan, e->ksplit_ws, e->ksplit_flags);
-                    if (opt.fuse && fused_into[i] < 0 && odt == DT_F32 && i + 1 < nl && net->layers[i + 1].type == YB_YOLO &&
-                        cons[i].size() == 1 && cons[i][0] == i + 1 && e->d_final[i + 1] && !getenv("YB_NO_YOLO_FUSE")) {
+                    if (fuse_yolo) {
                         tc_plan_fuse_yolo(plan, e->d_final[i + 1], net->layers[i + 1].classes);
                         yolo_fused[i + 1] = 1;
                     }
