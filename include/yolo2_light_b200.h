@@ -210,6 +210,19 @@ int yb_network_profile(yb_network *net, int quantized, const void *d_input, int 
 int yb_get_network_boxes(const yb_network *net, int b, int w, int h, float thresh, float nms, int relative,
                          int letter, float *out, int max_rows);
 
+/* ---- detection decode + NMS on the device, whole batch ------------------------------- */
+
+/* Same arithmetic as yb_get_network_boxes / the reference (get_yolo_detections src/additionally.c:4317,
+ * custom_get_region_detections :4363, correct_yolo_boxes :4281, do_nms_sort src/box.c:296), run on the yolo / region
+ * tensors where the last forward left them in HBM, for every image of the batch (the reference decodes batch item 0
+ * only).  rows: host float[batch][max_rows][5 + classes] = {x, y, w, h, objectness, prob[classes]} in the reference's
+ * candidate order (layer, cell, anchor); suppressed / below-threshold class entries are 0 like the reference leaves
+ * them.  counts[b] = number of candidates of image b; when it exceeds max_rows only the first max_rows candidates were
+ * decoded and took part in the NMS (the reference has no cap: size max_rows accordingly, <= 8192).
+ * Returns the row length 5 + classes, or -1. */
+int yb_network_detect(yb_network *net, int quantized, int w, int h, float thresh, float nms, int relative, int letter,
+                      float *rows, int max_rows, int *counts);
+
 const char *yb_version(void);
 
 #ifdef __cplusplus

@@ -89,6 +89,7 @@ def lib():
         "yb_network_set_precision": (C.c_int, [vp, C.c_int]),
         "yb_network_set_option": (C.c_int, [vp, C.c_char_p, C.c_int]),
         "yb_network_get_info": (C.c_long, [vp, C.c_int, C.c_char_p]),
+        "yb_network_detect": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, vp, C.c_int, vp]),
         "yb_network_predict": (fp, [vp, vp]),
         "yb_network_predict_quantized": (fp, [vp, vp]),
         "yb_network_predict_image_u8": (fp, [vp, vp, C.c_int, C.c_int, C.c_int]),
@@ -126,7 +127,7 @@ EXPORTED_SYMBOLS = [
     "yb_fuse_conv_batchnorm", "yb_calculate_binary_weights", "yb_quantinization_and_get_multipliers",
     "yb_network_from_layers", "yb_free_network", "yb_network_num_layers", "yb_network_dims", "yb_network_layer",
     "yb_network_layer_outputs", "yb_network_input_calibration", "yb_set_batch_network", "yb_network_set_device",
-    "yb_network_set_precision", "yb_network_set_option", "yb_network_get_info", "yb_network_predict", "yb_network_predict_quantized",
+    "yb_network_set_precision", "yb_network_set_option", "yb_network_get_info", "yb_network_detect", "yb_network_predict", "yb_network_predict_quantized",
     "yb_network_predict_image_u8", "yb_network_fetch_input", "yb_network_submit", "yb_network_collect", "yb_network_layer_output", "yb_network_forward_device", "yb_network_sync_outputs", "yb_network_fetch_layer",
     "yb_network_fetch_counts", "yb_forward_convolutional_layer", "yb_network_weight_arena",
     "yb_network_last_launches", "yb_network_profile", "yb_op_kind_name", "yb_get_network_boxes", "yb_alloc_pinned",
@@ -343,6 +344,23 @@ class Network:
                                        out.ctypes.data_as(C.c_void_p), max_rows)
         _check(r >= 0)
         return out[:min(r, max_rows)]
+
+
+    def detect(self, w: int, h: int, thresh: float, nms: float = 0.45, relative: int = 1, letter: int = 0,
+               max_rows: int = 1024, quantized: bool = False):
+        """Decode + NMS of the whole batch on the device (``yb_network_detect``).  Returns a list (one entry per image)
+        of float32 arrays [candidates, 5 + classes] and the raw candidate counts."""
+        classes = 0
+        for i in range(self.n):
+            d = self.layer_desc(i)
+            if d.type in (YB_YOLO, YB_REGION):
+                classes = d.classes
+        rows = np.zeros((self.batch, max_rows, 5 + classes), np.float32)
+        counts = np.zeros(self.batch, np.int32)
+        r = lib().yb_network_detect(self._h, int(quantized), w, h, thresh, nms, relative, letter,
+                                    rows.ctypes.data_as(C.c_void_p), max_rows, counts.ctypes.data_as(C.c_void_p))
+        _check(r == 5 + classes)
+        return [rows[b, :min(int(counts[b]), max_rows)] for b in range(self.batch)], counts
 
 
 # ---- the reference's function names -----------------------------------------------------------------------

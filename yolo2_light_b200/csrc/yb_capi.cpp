@@ -358,6 +358,13 @@ int yb_get_network_boxes(const yb_network *n, int b, int w, int h, float thresh,
     YB_CATCH(-1)
 }
 
+int yb_network_detect(yb_network *n, int quantized, int w, int h, float thresh, float nms, int relative, int letter,
+                      float *rows, int max_rows, int *counts) {
+    YB_TRY
+    return engine_detect(get_engine(n, quantized), &n->net, w, h, thresh, nms, relative, letter, rows, max_rows, counts);
+    YB_CATCH(-1)
+}
+
 /* pinned host memory for the end-to-end path (input images) */
 void *yb_alloc_pinned(size_t bytes);
 void yb_free_pinned(void *p);

@@ -16,6 +16,7 @@
 
 #include "yb_conv_tc.cuh"
 #include "yb_kernels.cuh"
+#include "yb_detect.cuh"
 
 namespace yb {
 
@@ -72,6 +73,9 @@ struct Engine {
     cudaGraphExec_t graph_exec = nullptr;
     bool graph_failed = false;
     std::vector<void *> tc_plans;      // opaque per-layer state of the tensor-core path (tensor maps)
+    // device-side decode + NMS workspace (engine_detect), sized for det_cap rows per image
+    float *det_rows = nullptr; unsigned *det_mask = nullptr; int *det_blkcnt = nullptr, *det_counts = nullptr;
+    int det_cap = 0, det_stride = 0, det_nblk = 0;
     int n_tc = 0, n_ksplit = 0;
     float *ksplit_ws = nullptr; unsigned *ksplit_flags = nullptr;   // partial sums / flags of the K-split tail (yb_conv_tc.cu)
     std::function<void(const float *, cudaStream_t)> first_op;   // consumes the caller's NCHW images (pointer varies per call)
@@ -99,6 +103,10 @@ Engine::~Engine() {
     for (int32_t *p : d_counts) if (p) cudaFree(p);
     for (void *p : tc_plans) tc_free_plan(p);
     if (stem_plan) tc_stem_free_plan(stem_plan);
+    if (det_rows) cudaFree(det_rows);
+    if (det_mask) cudaFree(det_mask);
+    if (det_blkcnt) cudaFree(det_blkcnt);
+    if (det_counts) cudaFree(det_counts);
     if (ksplit_ws) cudaFree(ksplit_ws);
     if (ksplit_flags) cudaFree(ksplit_flags);
     if (d_u8) cudaFree(d_u8);
@@ -1010,6 +1018,79 @@ int engine_fetch_counts(Engine *e, int layer, int32_t *dst, size_t count) {
 }
 
 void engine_weight_arena(Engine *e, void **ptr, size_t *bytes) { *ptr = e->w_arena; *bytes = e->w_bytes; }
+// Batched decode + NMS on the device (yb_detect.cuh).  rows: [batch][max_rows][5 + classes]; counts[b] = candidates of
+// image b before the max_rows cap.  Returns 5 + classes.
+int engine_detect(Engine *e, Network *net, int w, int h, float thresh, float nms, int relative, int letter,
+                  float *rows, int max_rows, int *counts) {
+    CUDA_OK(cudaSetDevice(e->opt.device));
+    if (max_rows <= 0 || max_rows > 8192) fatal_throw("detect: max_rows must be in 1..8192");
+    DetParams P{};
+    int total = 0;
+    for (size_t i = 0; i < net->layers.size(); ++i) {
+        const Layer &l = net->layers[i];
+        if (l.type != YB_YOLO && l.type != YB_REGION) continue;
+        if (!e->d_final[i]) fatal_throw("detect: detection layer has no device output");
+        if (P.nl == DET_MAX_LAYERS) fatal_throw("detect: too many detection layers");
+        if (l.n > DET_MAX_ANCHORS) fatal_throw("detect: too many anchors per layer");
+        if (P.nl && l.classes != P.classes) fatal_throw("detect: detection layers disagree on the class count");
+        DetLayer &d = P.L[P.nl++];
+        d.p = e->d_final[i]; d.type = l.type; d.w = l.w; d.h = l.h; d.n = l.n; d.classes = l.classes; d.outputs = l.outputs;
+        d.base = total; d.nbox = l.w * l.h * l.n; total += d.nbox;
+        for (int a = 0; a < l.n; ++a) {
+            const int k = (l.type == YB_YOLO) ? l.mask[a] : a;
+            d.aw[a] = l.anchors[2 * k]; d.ah[a] = l.anchors[2 * k + 1];
+        }
+        P.classes = l.classes;
+    }
+    if (!P.nl) fatal_throw("detect: the network has no yolo / region layer");
+    P.total = total; P.netw = net->w; P.neth = net->h; P.imw = w; P.imh = h; P.relative = relative;
+    P.new_w = net->w; P.new_h = net->h;
+    if (letter) {   // correct_yolo_boxes, additionally.c:4287-4296
+        if (((float)net->w / w) < ((float)net->h / h)) { P.new_w = net->w; P.new_h = (h * net->w) / w; }
+        else { P.new_h = net->h; P.new_w = (w * net->h) / h; }
+    }
+    P.thresh = thresh; P.nms = nms; P.max_rows = max_rows; P.nblk = (total + 255) / 256;
+    const int B = e->batch, stride = 5 + P.classes, words = (max_rows + 31) / 32;
+    if (e->det_cap < max_rows || e->det_stride != stride || e->det_nblk < P.nblk) {
+        if (e->det_rows) cudaFree(e->det_rows);
+        if (e->det_mask) cudaFree(e->det_mask);
+        if (e->det_blkcnt) cudaFree(e->det_blkcnt);
+        if (e->det_counts) cudaFree(e->det_counts);
+        CUDA_OK(cudaMalloc(&e->det_rows, (size_t)B * max_rows * stride * sizeof(float)));
+        CUDA_OK(cudaMalloc(&e->det_mask, (size_t)B * max_rows * words * sizeof(unsigned)));
+        CUDA_OK(cudaMalloc(&e->det_blkcnt, (size_t)B * P.nblk * sizeof(int)));
+        CUDA_OK(cudaMalloc(&e->det_counts, (size_t)B * sizeof(int)));
+        e->det_cap = max_rows; e->det_stride = stride; e->det_nblk = P.nblk;
+    }
+    P.max_rows = e->det_cap;   // row pitch of the workspace
+    const int cap = e->det_cap, capw = (cap + 31) / 32;
+    cudaStream_t s = e->stream;
+    k_det_count<<<dim3((unsigned)P.nblk, (unsigned)B), 256, 0, s>>>(P, e->det_blkcnt);
+    k_det_emit<<<dim3((unsigned)P.nblk, (unsigned)B), 256, 0, s>>>(P, e->det_blkcnt, e->det_rows, e->det_counts);
+    std::vector<int> hc(B);
+    CUDA_OK(cudaMemcpyAsync(hc.data(), e->det_counts, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    int nmax = 0;
+    for (int b = 0; b < B; ++b) { counts[b] = hc[b]; nmax = std::max(nmax, std::min(hc[b], cap)); }
+    if (nms > 0.f && nmax > 0) {
+        k_det_iou<<<dim3((unsigned)((capw + 127) / 128), (unsigned)nmax, (unsigned)B), 128, 0, s>>>(P, e->det_rows, e->det_counts, e->det_mask);
+        int P2 = 1; while (P2 < nmax) P2 <<= 1;
+        const size_t smem = (size_t)P2 * 8 + (size_t)capw * 4;
+        if (smem > 48 * 1024)
+            CUDA_OK(cudaFuncSetAttribute(k_det_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_det_nms<<<dim3((unsigned)P.classes, (unsigned)B), 256, smem, s>>>(P, e->det_rows, e->det_counts, e->det_mask, P2);
+    }
+    for (int b = 0; b < B; ++b) {
+        const int n = std::min(hc[b], std::min(cap, max_rows));
+        if (n > 0)
+            CUDA_OK(cudaMemcpyAsync(rows + (size_t)b * max_rows * stride, e->det_rows + (size_t)b * cap * stride,
+                                    (size_t)n * stride * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_OK(cudaStreamSynchronize(s));
+    CUDA_OK(cudaGetLastError());
+    return stride;
+}
+
 int engine_num_launches(Engine *e) { return (int)e->ops.size(); }
 long engine_info(Engine *e, const char *key) {
     if (!strcmp(key, "launches")) return (long)e->ops.size();

@@ -42,6 +42,8 @@ void engine_fetch_layer(Engine *e, Network *net, int layer, float *dst);
 void engine_fetch_input(Engine *e, float *dst);
 int engine_fetch_counts(Engine *e, int layer, int32_t *dst, size_t count);
 void engine_weight_arena(Engine *e, void **ptr, size_t *bytes);
+int engine_detect(Engine *e, Network *net, int w, int h, float thresh, float nms, int relative, int letter,
+                  float *rows, int max_rows, int *counts);   // device-side decode + NMS of the whole batch
 int engine_num_launches(Engine *e);
 long engine_info(Engine *e, const char *key);   // "launches", "tc_layers", "ksplit_layers"; -1 unknown
 int engine_profile(Engine *e, const void *d_input, int *layer_idx, int *op_kind, float *ms, int max);
