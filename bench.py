@@ -291,6 +291,23 @@ def main():
     h2d = batch * 3 * size * size * 4
     d2h = int(sum(o.size for o in net.detection_outputs().values()) * 4)
 
+    # ---- device-side decode + NMS of the batch (yb_network_detect; outside the timed step, reported beside it) ----
+    decode = None
+    if rank == 0:
+        try:
+            net.predict(pinned[0].array, quantized=bool(q))
+            cap = 1024
+            net.detect(size, size, 0.24, 0.45, max_rows=cap, quantized=bool(q))
+            t0 = time.perf_counter()
+            for _ in range(5):
+                dets, counts = net.detect(size, size, 0.24, 0.45, max_rows=cap, quantized=bool(q))
+            t_det = (time.perf_counter() - t0) / 5
+            decode = {"ms_per_batch": t_det * 1e3, "thresh": 0.24, "nms": 0.45, "max_rows": cap,
+                      "candidates_per_image": float(np.mean(counts)), "d2h_bytes": int(sum(d.nbytes for d in dets)),
+                      "note": "random-init heads put most boxes over the threshold; the cap bounds the NMS"}
+        except Exception as e:
+            decode = {"error": str(e)}
+
     # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), measured live with CUDA events ------
     roof = None
     if rank == 0:
@@ -357,7 +374,7 @@ def main():
                     "api": "yb_network_submit/collect (3 batches in flight, pinned host buffers)",
                     "sync_predict_value": batch * world / t_sync, "sync_predict_ms": t_sync * 1e3},
             "gpu_launches": launches_per_step * args.steps * world,
-            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "device_decode": decode,
             "tflops": conv_flops(secs, batch * world) * args.steps / (ms_total * 1e-3) / 1e12,
         }
         print(json.dumps(line), flush=True)
