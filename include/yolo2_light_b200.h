@@ -223,6 +223,21 @@ int yb_get_network_boxes(const yb_network *net, int b, int w, int h, float thres
 int yb_network_detect(yb_network *net, int quantized, int w, int h, float thresh, float nms, int relative, int letter,
                       float *rows, int max_rows, int *counts);
 
+/* ---- INT8 input calibration ---------------------------------------------------------- */
+
+/* network_calibrate_cpu (src/yolov2_forward_network.c:731-831) with the forward pass and the |x| histograms of every
+ * convolution's input on the GPU and entropy_calibration's KL search (src/yolov2_forward_network_quantized.c:1292-1398)
+ * restated on the host.  One call = one batch of calibration images: multipliers[b * nconv + k] is what the reference
+ * computes for image b at its k-th CONVOLUTIONAL layer (bin width 1/16, 4096 bins, :784).  Average over images and
+ * write them as `input_calibration = m0, m1, ..., 16` into the cfg (:753-769).  Uses the network's precision setting
+ * (YB_PREC_FP32 reproduces the reference's float activations); returns nconv, or -1. */
+int yb_network_calibrate(yb_network *net, const float *input, float *multipliers, int max_values);
+/* entropy_calibration (src/yolov2_forward_network_quantized.c:1292) on a host array: bit-identical multiplier. */
+float yb_entropy_calibration(const float *src, size_t size, float bin_width, int max_bin);
+/* |x| histogram of the input of layer `layer`, image `img`, after the last forward (diagnostic / tests). */
+int yb_network_input_histogram(yb_network *net, int quantized, int layer, int img, float bin_width, int max_bin,
+                               uint32_t *hist);
+
 const char *yb_version(void);
 
 #ifdef __cplusplus

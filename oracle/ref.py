@@ -143,6 +143,15 @@ class RefNet:
         return out[:min(n, max_out)]
 
 
+def entropy_calibration(src: np.ndarray, bin_width: float = 1.0 / 16, max_bin: int = 4096, kind: str = "scalar") -> float:
+    """The reference's entropy_calibration on one float array (prints one line to stdout, like the reference)."""
+    lib = _load(kind)
+    a = np.ascontiguousarray(src, dtype=np.float32).ravel()
+    lib.refh_entropy_calibration.restype = C.c_float
+    lib.refh_entropy_calibration.argtypes = [C.c_void_p, C.c_long, C.c_float, C.c_int]
+    return float(lib.refh_entropy_calibration(a.ctypes.data_as(C.c_void_p), a.size, bin_width, max_bin))
+
+
 def load_resize_u8(img_hwc: np.ndarray, out_w: int, out_h: int, kind: str = "scalar") -> np.ndarray:
     """The reference's load_image_stb conversion + resize_image on one u8 HWC image -> float32[c, out_h, out_w]."""
     lib = _load(kind)

@@ -223,6 +223,14 @@ void refh_im2col(float *im, int c, int hgt, int w, int k, int stride, int pad, f
     im2col_cpu(im, c, hgt, w, k, stride, pad, col);   /* additionally.c:39 */
 }
 
+/* INT8 input calibration: the reference's KL search, yolov2_forward_network_quantized.c:1292-1398,
+ * with the arguments network_calibrate_cpu uses (yolov2_forward_network.c:784: bin width 1/16, 4096 bins). */
+float entropy_calibration(float *src_arr, const size_t size, const float bin_width, const int max_bin);
+float refh_entropy_calibration(float *src, long size, float bin_width, int max_bin)
+{
+    return entropy_calibration(src, (size_t)size, bin_width, max_bin);
+}
+
 /* Image pipeline of the reference app: u8 HWC (what stbi_load returns) -> planar float /255. (load_image_stb,
  * additionally.c:3080-3103) -> resize_image bilinear to the network size (additionally.c:3021-3064, only when the
  * size differs, load_image :3066-3078).  out: float[c*out_h*out_w]. */

@@ -310,3 +310,46 @@ def test_device_input_pipeline_bit_exact(src_hw, workdir):
     net.predict(exp)
     for i, o in net.detection_outputs().items():
         assert util.bits_equal(o, a[i])
+
+
+@pytest.mark.parametrize("name", ["tiny64", "v3_32"])
+def test_int8_calibration_on_device(name, workdir):
+    """|x| histograms of every convolution input on the GPU (exact integers) + the reference's KL
+    search; multipliers against entropy_calibration run by the reference on ITS activations, image by image."""
+    import yolo2_light_b200 as yb
+    from oracle import ref
+    B = 2
+    cfg, wts = util.model_files(name, workdir)
+    x = util.images(name, B)
+    net = yb.load_network(cfg, wts, batch=B)
+    net.set_precision(yb.YB_PREC_FP32)
+    # (1) the histogram kernel counts exactly what the reference's binning counts
+    net.set_option("fuse", 0)
+    net.predict(x)
+    convs = [i for i, l in enumerate(net.layers) if l["type_name"] == "CONVOLUTIONAL"]
+    for i in convs[:6]:
+        for b in range(B):
+            src = x[b] if i == 0 else net.fetch_layer(i - 1)[b]
+            bins = np.minimum(np.floor(np.abs(src.astype(np.float64)) * 16.0 + 0.5).astype(np.int64), 4095)
+            exp = np.bincount(bins.ravel(), minlength=4096).astype(np.uint32)
+            assert np.array_equal(net.input_histogram(i, b), exp), (i, b)
+    # (2) whole tool
+    mult = net.calibrate(x)
+    assert mult.shape == (B, len(convs)) and np.all(mult > 0)
+    rnet = ref.RefNet(cfg, wts, 1, 0, 7)
+    same = total = 0
+    for b in range(B):
+        rnet.predict(x[b:b + 1])
+        for k, i in enumerate(convs):
+            src = x[b] if i == 0 else rnet.output(i - 1)
+            theirs = ref.entropy_calibration(src)
+            total += 1
+            same += np.float32(theirs) == mult[b, k]
+            # activations differ in the last bit (f32 summation order): a count may cross a bin edge and move the optimum
+            assert abs(mult[b, k] - theirs) <= 0.05 * theirs, (b, i, mult[b, k], theirs)
+    assert same >= 0.8 * total, (same, total)
+    line = yb.api.format_input_calibration(mult)
+    assert line.startswith("input_calibration = ") and line.endswith(", 16") and line.count(",") == len(convs)
+    # the engine is back in its normal (fused) configuration and still right
+    net.set_option("fuse", 1)
+    net.predict(x)

@@ -109,8 +109,8 @@ int main() {
     cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     const int iters = 512;
     printf("%5s %5s %3s | %12s %12s\n", "N", "nacc", "kk", "issue cyc/MMA", "total cyc/MMA");
-    for (int mode : {0})
-    for (int kk : {8, 32})
+    for (int mode : {0, 1})
+    for (int kk : {1, 4, 8, 32})
         for (int N : {32, 64, 128, 256})
             for (int nacc : {1, 2}) {
                 if (nacc * N > 512) continue;

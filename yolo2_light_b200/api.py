@@ -89,6 +89,9 @@ def lib():
         "yb_network_set_precision": (C.c_int, [vp, C.c_int]),
         "yb_network_set_option": (C.c_int, [vp, C.c_char_p, C.c_int]),
         "yb_network_get_info": (C.c_long, [vp, C.c_int, C.c_char_p]),
+        "yb_network_calibrate": (C.c_int, [vp, vp, vp, C.c_int]),
+        "yb_entropy_calibration": (C.c_float, [vp, C.c_size_t, C.c_float, C.c_int]),
+        "yb_network_input_histogram": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp]),
         "yb_network_detect": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, vp, C.c_int, vp]),
         "yb_network_predict": (fp, [vp, vp]),
         "yb_network_predict_quantized": (fp, [vp, vp]),
@@ -127,7 +130,8 @@ EXPORTED_SYMBOLS = [
     "yb_fuse_conv_batchnorm", "yb_calculate_binary_weights", "yb_quantinization_and_get_multipliers",
     "yb_network_from_layers", "yb_free_network", "yb_network_num_layers", "yb_network_dims", "yb_network_layer",
     "yb_network_layer_outputs", "yb_network_input_calibration", "yb_set_batch_network", "yb_network_set_device",
-    "yb_network_set_precision", "yb_network_set_option", "yb_network_get_info", "yb_network_detect", "yb_network_predict", "yb_network_predict_quantized",
+    "yb_network_set_precision", "yb_network_set_option", "yb_network_get_info", "yb_network_detect", "yb_network_calibrate", "yb_entropy_calibration",
+    "yb_network_input_histogram", "yb_network_predict", "yb_network_predict_quantized",
     "yb_network_predict_image_u8", "yb_network_fetch_input", "yb_network_submit", "yb_network_collect", "yb_network_layer_output", "yb_network_forward_device", "yb_network_sync_outputs", "yb_network_fetch_layer",
     "yb_network_fetch_counts", "yb_forward_convolutional_layer", "yb_network_weight_arena",
     "yb_network_last_launches", "yb_network_profile", "yb_op_kind_name", "yb_get_network_boxes", "yb_alloc_pinned",
@@ -346,6 +350,24 @@ class Network:
         return out[:min(r, max_rows)]
 
 
+    def calibrate(self, images: np.ndarray) -> np.ndarray:
+        """INT8 input calibration of one image batch (``yb_network_calibrate``): float32[batch, nconv] multipliers."""
+        x = np.ascontiguousarray(images, dtype=np.float32)
+        if x.size != self.batch * self.c * self.h * self.w:
+            raise YbError(f"calibrate: expected {self.batch}x{self.c}x{self.h}x{self.w} floats, got {x.size}")
+        nconv = sum(1 for i in range(self.n) if self.layer_desc(i).type == YB_CONVOLUTIONAL)
+        out = np.zeros((self.batch, nconv), np.float32)
+        r = lib().yb_network_calibrate(self._h, x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), out.size)
+        _check(r == nconv)
+        return out
+
+    def input_histogram(self, layer: int, img: int = 0, bin_width: float = 1.0 / 16, max_bin: int = 4096,
+                        quantized: bool = False) -> np.ndarray:
+        h = np.zeros(max_bin, np.uint32)
+        _check(lib().yb_network_input_histogram(self._h, int(quantized), layer, img, bin_width, max_bin,
+                                                h.ctypes.data_as(C.c_void_p)) == 0)
+        return h
+
     def detect(self, w: int, h: int, thresh: float, nms: float = 0.45, relative: int = 1, letter: int = 0,
                max_rows: int = 1024, quantized: bool = False):
         """Decode + NMS of the whole batch on the device (``yb_network_detect``).  Returns a list (one entry per image)
@@ -361,6 +383,22 @@ class Network:
                                     rows.ctypes.data_as(C.c_void_p), max_rows, counts.ctypes.data_as(C.c_void_p))
         _check(r == 5 + classes)
         return [rows[b, :min(int(counts[b]), max_rows)] for b in range(self.batch)], counts
+
+
+def entropy_calibration(src: np.ndarray, bin_width: float = 1.0 / 16, max_bin: int = 4096) -> float:
+    """``entropy_calibration`` of the reference (yolov2_forward_network_quantized.c:1292) on a host array."""
+    a = np.ascontiguousarray(src, dtype=np.float32).ravel()
+    r = float(lib().yb_entropy_calibration(a.ctypes.data_as(C.c_void_p), a.size, bin_width, max_bin))
+    _check(r > 0)
+    return r
+
+
+def format_input_calibration(multipliers: np.ndarray) -> str:
+    """The cfg line the reference writes to input_calibration.txt (yolov2_forward_network.c:753-769): per-convolution
+    means over the calibration images printed with %g, closed by its constant 16."""
+    m = np.asarray(multipliers, np.float32).reshape(-1, np.asarray(multipliers).shape[-1])
+    mean = m.sum(axis=0, dtype=np.float32) / np.float32(m.shape[0])
+    return "input_calibration = " + "".join("%g, " % v for v in mean) + "16"
 
 
 # ---- the reference's function names -----------------------------------------------------------------------

@@ -365,6 +365,50 @@ int yb_network_detect(yb_network *n, int quantized, int w, int h, float thresh, 
     YB_CATCH(-1)
 }
 
+/* INT8 input calibration: one forward (FP32 rule) + per-convolution |input| histograms on the GPU + the reference's
+ * KL search on the host.  multipliers[b * nconv + k] for image b and the k-th CONVOLUTIONAL layer. */
+int yb_network_calibrate(yb_network *n, const float *input, float *multipliers, int max_values) {
+    YB_TRY
+    Network &net = n->net;
+    const bool old_fuse = net.fuse;
+    if (old_fuse) { net.fuse = false; net.engine[0].reset(); }          // every layer input must exist in memory
+    Engine *e = get_engine(n, 0);
+    engine_upload_input(e, input, nullptr);
+    engine_forward(e, nullptr, nullptr);
+    int nconv = 0;
+    for (const Layer &l : net.layers) nconv += l.type == YB_CONVOLUTIONAL;
+    if (max_values < nconv * net.batch) fatal_throw("calibrate: multipliers[] too small");
+    std::vector<uint32_t> hist(4096);
+    for (int b = 0; b < net.batch; ++b) {
+        int k = 0;
+        for (size_t i = 0; i < net.layers.size(); ++i) {
+            if (net.layers[i].type != YB_CONVOLUTIONAL) continue;
+            // network_calibrate_cpu, yolov2_forward_network.c:784: entropy_calibration(state.input, l.inputs, 1.0 / 16, 4096)
+            engine_input_histogram(e, &net, (int)i, b, 1.0f / 16, 4096, hist.data());
+            multipliers[(size_t)b * nconv + k++] = entropy_from_histogram(hist.data(), 1.0f / 16, 4096);
+        }
+    }
+    if (old_fuse) { net.fuse = true; net.engine[0].reset(); }
+    return nconv;
+    YB_CATCH(-1)
+}
+/* the host half alone (histogram + KL search of one array), == entropy_calibration(src, size, bin_width, max_bin) */
+float yb_entropy_calibration(const float *src, size_t size, float bin_width, int max_bin) {
+    YB_TRY
+    if (max_bin < 129 || max_bin > 1 << 20) fatal_throw("entropy_calibration: bad max_bin");
+    std::vector<uint32_t> hist(max_bin);
+    abs_histogram_host(src, size, bin_width, max_bin, hist.data());
+    return entropy_from_histogram(hist.data(), bin_width, max_bin);
+    YB_CATCH(-1.f)
+}
+/* histogram of the input of layer i for image b after the last forward (GPU), for tests */
+int yb_network_input_histogram(yb_network *n, int quantized, int layer, int img, float bin_width, int max_bin, uint32_t *hist) {
+    YB_TRY
+    engine_input_histogram(get_engine(n, quantized), &n->net, layer, img, bin_width, max_bin, hist);
+    return 0;
+    YB_CATCH(-1)
+}
+
 /* pinned host memory for the end-to-end path (input images) */
 void *yb_alloc_pinned(size_t bytes);
 void yb_free_pinned(void *p);

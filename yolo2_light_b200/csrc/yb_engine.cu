@@ -1018,6 +1018,31 @@ int engine_fetch_counts(Engine *e, int layer, int32_t *dst, size_t count) {
 }
 
 void engine_weight_arena(Engine *e, void **ptr, size_t *bytes) { *ptr = e->w_arena; *bytes = e->w_bytes; }
+// INT8 input calibration: |x| histogram of the INPUT of layer `layer` (image `img` of the batch) after a
+// forward, binned like the reference's entropy_calibration.  hist: host uint32[max_bin].
+void engine_input_histogram(Engine *e, Network *net, int layer, int img, float bin_width, int max_bin, uint32_t *hist) {
+    CUDA_OK(cudaSetDevice(e->opt.device));
+    if (max_bin < 129 || max_bin > 4096) fatal_throw("calibrate: max_bin must be in 129..4096");
+    if (img < 0 || img >= e->batch) fatal_throw("calibrate: image index out of range");
+    unsigned *d_hist = nullptr;
+    CUDA_OK(cudaMalloc(&d_hist, (size_t)max_bin * sizeof(unsigned)));
+    CUDA_OK(cudaMemsetAsync(d_hist, 0, (size_t)max_bin * sizeof(unsigned), e->stream));
+    if (layer == 0) {
+        const long n = (long)net->c * net->h * net->w;
+        k_abs_hist_flat<<<grid_for(n), 256, 0, e->stream>>>(e->d_input + (size_t)img * n, n, bin_width, max_bin, d_hist);
+    } else {
+        const TV t = e->out_tv[layer - 1];
+        if (!t.base) { cudaFree(d_hist); fatal_throw("calibrate: the input of layer " + std::to_string(layer) +
+                                                     " is not materialised (fused away; set option fuse=0)"); }
+        const long n = (long)t.C * t.H * t.W;
+        if (e->out_dt[layer - 1] == DT_F32) k_abs_hist<float><<<grid_for(n), 256, 0, e->stream>>>(t, img, bin_width, max_bin, d_hist);
+        else k_abs_hist<__nv_bfloat16><<<grid_for(n), 256, 0, e->stream>>>(t, img, bin_width, max_bin, d_hist);
+    }
+    CUDA_OK(cudaMemcpyAsync(hist, d_hist, (size_t)max_bin * sizeof(unsigned), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    cudaFree(d_hist);
+}
+
 // Batched decode + NMS on the device (yb_detect.cuh).  rows: [batch][max_rows][5 + classes]; counts[b] = candidates of
 // image b before the max_rows cap.  Returns 5 + classes.
 int engine_detect(Engine *e, Network *net, int w, int h, float thresh, float nms, int relative, int letter,

@@ -894,4 +894,45 @@ __global__ void k_region(TV in, float *__restrict__ out, int nanchors, int class
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// INT8 input calibration: histogram of |x| over the logical elements of image `img` of an
+// activation tensor, binned exactly like the reference (yolov2_forward_network_quantized.c:1308-1316:
+// lround(fabs(x) / bin_width) in double, saturated into the last bin).  Per-block shared-memory histogram,
+// integer atomics -> exact counts.  max_bin <= 4096.
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_abs_hist(TV in, int img, float bin_width, int max_bin, unsigned *__restrict__ hist) {
+    __shared__ unsigned sh[4096];
+    for (int i = threadIdx.x; i < max_bin; i += 256) sh[i] = 0u;
+    __syncthreads();
+    const long per = (long)in.C * in.H * in.W;
+    const int last_bin = max_bin - 1;
+    for (long e = (long)blockIdx.x * 256 + threadIdx.x; e < per; e += (long)gridDim.x * 256) {
+        const int c = (int)(e % in.C);
+        const long px = e / in.C;
+        const int x = (int)(px % in.W), y = (int)(px / in.W);
+        const float v = to_f32(tv_px<T>(in, img, y, x)[c]);
+        const long b = lround(fabs((double)v) / (double)bin_width);
+        atomicAdd(&sh[b >= last_bin ? last_bin : (int)b], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < max_bin; i += 256)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+// the network input (NCHW f32, as the caller passes it)
+static __global__ void __launch_bounds__(256) k_abs_hist_flat(const float *__restrict__ src, long n, float bin_width, int max_bin,
+                                                              unsigned *__restrict__ hist) {
+    __shared__ unsigned sh[4096];
+    for (int i = threadIdx.x; i < max_bin; i += 256) sh[i] = 0u;
+    __syncthreads();
+    const int last_bin = max_bin - 1;
+    for (long e = (long)blockIdx.x * 256 + threadIdx.x; e < n; e += (long)gridDim.x * 256) {
+        const long b = lround(fabs((double)src[e]) / (double)bin_width);
+        atomicAdd(&sh[b >= last_bin ? last_bin : (int)b], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < max_bin; i += 256)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
 }  // namespace yb

@@ -6,6 +6,7 @@
 #include "yb_model.h"
 
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -551,6 +552,70 @@ int get_boxes(const Network *net, int b, int w, int h, float thresh, float nms, 
         for (int c = 0; c < classes; ++c) o[5 + c] = dets[i].prob[c];
     }
     return (int)dets.size();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// INT8 input calibration.  entropy_calibration, yolov2_forward_network_quantized.c:1292-1398, from
+// the |x| histogram (hist[b] = #elements with lround(fabs(x) / bin_width) == b, saturated into the last bin -- the part
+// that touches the data and runs on the GPU).  Types and conversions follow the C source (float histogram and P/Q
+// arrays, uint64 "outliers" updated through float arithmetic, double log, float accumulator), so the multiplier is
+// bit-identical to the reference's for the same histogram.
+// ------------------------------------------------------------------------------------------------------
+float entropy_from_histogram(const uint32_t *hist, float bin_width, int max_bin) {
+    std::vector<float> m_array(max_bin, 0.f), H(max_bin), P(max_bin, 0.f), Q(max_bin, 0.f);
+    float quant_Q[128];
+    uint64_t quant_cnt[128];
+    for (int j = 0; j < max_bin; ++j) {
+        // the reference counts with `float++`: exact up to 2^24, stuck there afterwards
+        H[j] = (float)std::min<uint32_t>(hist[j], 16777216u);
+    }
+    for (int i = 128; i < max_bin; ++i) {
+        uint64_t outliers = 0;
+        const int last_bin = i - 1;
+        for (int j = 0; j <= last_bin; ++j) P[j] = 0;
+        for (int j = 0; j < max_bin; ++j) {
+            if (j <= last_bin) P[j] = H[j];
+            else outliers = (uint64_t)((float)outliers + H[j]);      // `outliers += H_histogram[j]` (float arithmetic)
+        }
+        const float quant_expand_width = i / 128.0F;
+        for (int j = 0; j < 128; ++j) { quant_Q[j] = 0; quant_cnt[j] = 0; }
+        for (int j = 0; j < i; ++j) {
+            int quant_bin = (int)lround((double)(j / quant_expand_width));
+            if (quant_bin > 127) quant_bin = 127;
+            quant_Q[quant_bin] += P[j];
+            if (P[j] != 0) quant_cnt[quant_bin]++;
+        }
+        for (int j = 0; j < i; ++j) Q[j] = 0;
+        for (int j = 0; j < i; ++j) {
+            int quant_bin = (int)lround((double)(j / quant_expand_width));
+            if (quant_bin > 127) quant_bin = 127;
+            if (P[j] != 0) Q[j] = quant_Q[quant_bin] / (float)quant_cnt[quant_bin];
+        }
+        P[last_bin] = P[last_bin] + (float)outliers;                  // saturation
+        float sum_P = 0, sum_Q = 0;
+        for (int j = 0; j < i; ++j) { sum_P += P[j]; sum_Q += Q[j]; }
+        for (int j = 0; j < i; ++j) { P[j] /= sum_P; Q[j] /= sum_Q; }
+        for (int j = 0; j < i; ++j) {
+            const float ratio = (P[j] + FLT_MIN) / (Q[j] + FLT_MIN);
+            m_array[i] = (float)((double)m_array[i] + (double)P[j] * log((double)ratio));
+        }
+    }
+    float m_index = 128, min_m = FLT_MAX;
+    for (int i = 128; i < max_bin; ++i)
+        if (m_array[i] < min_m) { min_m = m_array[i]; m_index = (float)i; }
+    const float threshold = (float)(((double)m_index + 0.5) * (double)bin_width);
+    return 127 / threshold;
+}
+
+// host histogram with the reference's binning (yolov2_forward_network_quantized.c:1308-1316); the GPU kernel
+// k_abs_hist computes the same integers
+void abs_histogram_host(const float *src, size_t n, float bin_width, int max_bin, uint32_t *hist) {
+    const int last_bin = max_bin - 1;
+    for (int j = 0; j < max_bin; ++j) hist[j] = 0;
+    for (size_t j = 0; j < n; ++j) {
+        const long bin_num = lround(fabs((double)src[j]) / (double)bin_width);
+        hist[bin_num >= last_bin ? last_bin : (int)bin_num]++;
+    }
 }
 
 }  // namespace yb

@@ -67,6 +67,9 @@ void set_batch(Network *net, int batch);
 int get_boxes(const Network *net, int b, int w, int h, float thresh, float nms, int relative, int letter,
               float *out, int max_rows);
 
+float entropy_from_histogram(const uint32_t *hist, float bin_width, int max_bin);
+void abs_histogram_host(const float *src, size_t n, float bin_width, int max_bin, uint32_t *hist);
+
 }  // namespace yb
 
 struct yb_network {
