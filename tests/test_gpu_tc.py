@@ -187,3 +187,31 @@ def test_tc_ksplit_tail_matches_plain_schedule(h, w, batch, workdir):
         net.predict(x); ref.predict(x)
     for i, o in net.detection_outputs().items():
         assert util.rel_l2(o, ref.detection_outputs()[i]) <= 2e-3, i
+
+
+@pytest.mark.parametrize("name,q", [("tiny64", 1), ("xnor64", 0), ("tiny_w96_h64", 1)])
+def test_tf32_heads_of_exact_networks(name, q, workdir):
+    """The float detection heads of the INT8 / XNOR networks run on tcgen05 kind::tf32 in the default precision (their
+    result feeds no integer layer); everything upstream stays bit-exact, the detections stay within the FP32 bar of
+    the all-f32 engine (north_star: <= 1e-3 rel)."""
+    import yolo2_light_b200 as yb
+    cfg, wts = util.model_files(name, workdir)
+    B = 3
+    x = util.images(name, B)
+    fast = yb.load_network(cfg, wts, batch=B, quantized=q)
+    fast.predict(x, quantized=bool(q))
+    kinds = [k for _, k, _ in fast.profile(quantized=bool(q))]
+    assert "conv_tc_tf32" in kinds, kinds
+    exact = yb.load_network(cfg, wts, batch=B, quantized=q)
+    exact.set_precision(yb.YB_PREC_FP32)
+    exact.predict(x, quantized=bool(q))
+    assert "conv_tc_tf32" not in [k for _, k, _ in exact.profile(quantized=bool(q))]
+    for i, o in fast.detection_outputs().items():
+        err = util.rel_l2(o, exact.detection_outputs()[i])
+        assert err <= 1e-3, (name, i, err)
+    # the integer layers did not notice: raw accumulators / counts of the last integer layer are identical
+    fast.set_option("keep_counts", 1); exact.set_option("keep_counts", 1)
+    fast.predict(x, quantized=bool(q)); exact.predict(x, quantized=bool(q))
+    ints = [i for i, l in enumerate(fast.layers) if l["type_name"] == "CONVOLUTIONAL" and (l["xnor"] or (q and i >= 1 and l["activation"] != 3))]
+    a = fast.fetch_counts(ints[-1], quantized=bool(q)); b = exact.fetch_counts(ints[-1], quantized=bool(q))
+    assert a is not None and np.array_equal(a, b)

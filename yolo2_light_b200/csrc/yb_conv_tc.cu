@@ -47,7 +47,8 @@ struct TcParams {
     int num_work;             // work items of the persistent loop: num_tiles (CG=1) or pairs of m-tiles x nt (CG=2)
     int cg;                   // 1, or 2 = CTA pairs (cta_group::2)
     int kind;                 // 0: bf16 x bf16 -> f32 (kind::f16);  1: s8 x s8 -> s32 (kind::i8), exact requantising epilogue;
-                              // 2: XNOR layer as +-1 s8 on kind::i8 (dot = 2*count - K exactly), reference float epilogue
+                              // 2: XNOR layer as +-1 s8 on kind::i8 (dot = 2*count - K exactly), reference float epilogue;
+                              // 3: f32 operands read as tf32 (kind::tf32, K = 8 per MMA) -> f32: float heads of the exact nets
     int kk;                   // MMAs per K-block (BK bytes / 32)
     float alpha1;             // INT8: R_MULT / (input_mult * weights_mult)
     const float *mean;        // kind 2 (XNOR as +-1 s8): per-filter mean |w|; out = (float)dot * mean + bias
@@ -153,6 +154,12 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -442,6 +449,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         const int first = (kb0 - kb_begin) | j;     // 0 on the first K-block of the segment: overwrite the accumulator
                         for (int k = 0; k < kk; ++k) {
                             if constexpr (CG == 2) umma2_bf16(d_tmem, adesc, bdesc, idesc, (uint32_t)((first | k) != 0));
+                            else if (kind == 3) umma_tf32(d_tmem, adesc, bdesc, idesc, (uint32_t)((first | k) != 0));
                             else if (kind != 0) umma_i8(d_tmem, adesc, bdesc, idesc, (uint32_t)((first | k) != 0));
                             else umma_bf16(d_tmem, adesc, bdesc, idesc, (uint32_t)((first | k) != 0));
                             adesc += 2; bdesc += 2;
@@ -1045,6 +1053,7 @@ struct TcPlan {
 
 int pick_bk(int C) { return (C % 64 == 0) ? 64 : (C % 32 == 0) ? 32 : (C % 16 == 0) ? 16 : 0; }
 int pick_bk_i8(int cpad) { return (cpad % 128 == 0) ? 128 : (cpad % 64 == 0) ? 64 : (cpad % 32 == 0) ? 32 : 0; }
+int pick_bk_f32(int C) { return (C % 32 == 0) ? 32 : (C % 16 == 0) ? 16 : (C % 8 == 0) ? 8 : 0; }
 int pick_bn(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : 256; }
 
 }  // namespace
@@ -1069,9 +1078,10 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
     TcPlan *plan = new TcPlan();
     memset(plan, 0, sizeof(*plan));
     TcParams &p = plan->p;
-    const int esz = kind != 0 ? 1 : 2;                       // operand element size
-    const int cin = kind != 0 ? in.ldc : l.c;                // s8: channels padded with zeros in both operands
-    const int BK = kind != 0 ? pick_bk_i8(cin) : pick_bk(l.c), BN = pick_bn(l.n);
+    const bool i8 = kind == 1 || kind == 2;
+    const int esz = kind == 3 ? 4 : i8 ? 1 : 2;              // operand element size
+    const int cin = i8 ? in.ldc : l.c;                       // s8: channels padded with zeros in both operands
+    const int BK = kind == 3 ? pick_bk_f32(l.c) : i8 ? pick_bk_i8(cin) : pick_bk(l.c), BN = pick_bn(l.n);
     p.kind = kind; p.alpha1 = alpha1; p.acc_out = acc_out;
     p.kk = BK * esz / 32;
     const bool s2 = l.stride == 2;
@@ -1137,7 +1147,9 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
     // UMMA instruction descriptor (kind::f16): D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TC_BM * p.cg) >> 4) << 24);
     // kind::i8: D = s32 (2 at bit 4), A = B = signed 8 bit (1 at bits 7 / 10)
-    if (kind != 0) p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    if (i8) p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    // kind::tf32: D = f32, A = B = tf32 (format 2): the tensor core reads the f32 words in place
+    if (kind == 3) p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     // smem descriptor high word: SBO (8 rows * row bytes) >> 4 at bits 32..45, version 1 at bit 46, swizzle at 61..63
     const uint32_t row_bytes = (uint32_t)(BK * esz);
     const uint32_t layout = row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;
@@ -1160,7 +1172,8 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
     const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                  : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
     EncodeTiledFn enc = encode_fn();
-    const CUtensorMapDataType dtype = kind != 0 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const CUtensorMapDataType dtype = kind == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                    : i8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     CUresult r;
     if (!s2) {
         // activation view (c, x_padded, merged padded rows)
@@ -1213,6 +1226,25 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
 void *tc_make_plan(const Layer &l, const TV &in, const TV &out, bool out_bf16, const TV &res, bool res_bf16,
                    int act2, const void *d_weights_bf16, int ldn, const float *d_bias, int wide_rows) {
     return make_plan_common(0, l, in, out, out_bf16, res, res_bf16, act2, d_weights_bf16, ldn, d_bias, 0.f, nullptr, wide_rows);
+}
+
+// FP32 convolution of the exact (INT8 / XNOR) networks on kind::tf32: f32 NHWC activations and f32 [ldn][K] weights go
+// through TMA untouched, the tensor core uses the upper 19 bits of each word (10-bit mantissa, ~3e-4 relative on the
+// sums).  Used for detection heads only (their error cannot reach an integer layer), f32 output.
+int tc_tf32_supported(const Layer &l, const TV &in, const TV &out) {
+    if (pick_bk_f32(l.c) == 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(in.base) & 15) != 0 || in.P != 1 || in.ldc % 4 != 0) return 0;
+    const bool s1 = l.stride == 1 && ((l.size == 3 && l.pad == 1) || (l.size == 1 && l.pad == 0));
+    const bool s2 = l.stride == 2 && l.size == 3 && l.pad == 1 && (l.h % 2 == 0) && (l.w % 2 == 0);
+    if (!s1 && !s2) return 0;
+    if (!out.base || (reinterpret_cast<uintptr_t>(out.base) & 15) != 0 || out.ldc % 4 != 0 || l.n < 8) return 0;
+    if (l.activation != YB_LEAKY && l.activation != YB_LINEAR) return 0;
+    return 1;
+}
+void *tc_make_plan_tf32(const Layer &l, const TV &in, const TV &out, const void *d_weights_f32, int ldn, const float *d_bias,
+                        int wide_rows) {
+    TV none{};
+    return make_plan_common(3, l, in, out, false, none, false, ACT_LINEAR, d_weights_f32, ldn, d_bias, 0.f, nullptr, wide_rows);
 }
 
 // INT8 variant (reference forward_convolutional_layer_q, yolov2_forward_network_quantized.c:527-631) on

@@ -31,8 +31,8 @@ namespace yb {
 const char *op_kind_name(int k) {
     static const char *names[] = {"input", "conv_simt", "conv_tc", "binarize", "conv_xnor", "quantize",
                                   "conv_int8", "maxpool", "upsample", "shortcut", "route_copy", "reorg",
-                                  "yolo", "region", "conv_tc_i8", "conv_tc2"};
-    return (k >= 0 && k < 16) ? names[k] : "?";
+                                  "yolo", "region", "conv_tc_i8", "conv_tc2", "conv_tc_tf32"};
+    return (k >= 0 && k < 17) ? names[k] : "?";
 }
 
 enum { DT_F32 = 0, DT_BF16 = 1, DT_S8 = 2, DT_BITS = 3 };
@@ -46,6 +46,7 @@ struct Op {
 
 struct ConvWeights {   // offsets into the weight arena
     size_t w_f32 = (size_t)-1, w_bf16 = (size_t)-1, w_s8 = (size_t)-1, w_bits = (size_t)-1;
+    size_t w_f32km = (size_t)-1;   // f32 [ldn][K], K-major (kind::tf32)
     size_t bias = (size_t)-1, mean = (size_t)-1;
     int ldw = 0;      // f32 [K][ldw]
     int ldn = 0;      // rows of the [ldn][...] layouts
@@ -398,8 +399,24 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
             const int odt = fused_into[i] >= 0 ? e->out_dt[fused_into[i]] : e->out_dt[i];
             const TV &tout = e->out_tv[fused_into[i] >= 0 ? fused_into[i] : i];
             use_tc[i] = (ADT == DT_BF16 && in_dt == DT_BF16) ? tc_conv_supported(l, tin, tout, odt == DT_BF16) : 0;
+            // float detection heads of the INT8 / XNOR networks (default precision): kind::tf32.  Only layers whose every
+            // reader is a yolo / region layer -- nothing they compute can reach an integer layer.
+            if (ADT == DT_F32 && opt.precision == YB_PREC_BF16_TC && in_dt == DT_F32 && odt == DT_F32 && fused_into[i] < 0 &&
+                !cons[i].empty() && !getenv("YB_NO_TF32")) {
+                bool heads_only = true;
+                for (int r : cons[i]) heads_only &= net->layers[r].type == YB_YOLO || net->layers[r].type == YB_REGION;
+                if (heads_only && tc_tf32_supported(l, tin, tout)) use_tc[i] = 2;
+            }
             if (getenv("YB_NO_TC")) use_tc[i] = 0;
-            if (use_tc[i]) {
+            if (use_tc[i] == 2) {
+                w.ldn = (int)align_up(l.n, 64);
+                w.w_f32km = reserve(sizeof(float) * (size_t)w.ldn * K);
+                float *dst = reinterpret_cast<float *>(&hostw[w.w_f32km]);
+                for (int f = 0; f < l.n; ++f)
+                    for (int c = 0; c < l.c; ++c)
+                        for (int t = 0; t < taps; ++t)
+                            dst[(size_t)f * K + (size_t)t * l.c + c] = l.weights[((size_t)f * l.c + c) * taps + t];
+            } else if (use_tc[i]) {
                 // bf16 [ldn][K], K ordered (ky, kx, c): the K-major B operand of the implicit GEMM
                 w.ldn = (int)align_up(l.n, 64);
                 w.w_bf16 = reserve(sizeof(__nv_bfloat16) * (size_t)w.ldn * K);
@@ -561,7 +578,19 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                     act2 = s.activation;
                     if (!res.base) fatal_throw("engine: shortcut source not placed");
                 }
-                if (use_tc[i]) {
+                if (use_tc[i] == 2) {
+                    const bool fuse_yolo = opt.fuse && i + 1 < nl && net->layers[i + 1].type == YB_YOLO && cons[i].size() == 1 &&
+                                           cons[i][0] == i + 1 && e->d_final[i + 1] && !getenv("YB_NO_YOLO_FUSE");
+                    void *plan = tc_make_plan_tf32(l, tin, tout, e->w_arena + cw[i].w_f32km, cw[i].ldn,
+                                                   reinterpret_cast<const float *>(e->w_arena + cw[i].bias), fuse_yolo ? 1 : 0);
+                    e->tc_plans.push_back(plan);
+                    ++e->n_tc;
+                    if (fuse_yolo) {
+                        tc_plan_fuse_yolo(plan, e->d_final[i + 1], net->layers[i + 1].classes);
+                        yolo_fused[i + 1] = 1;
+                    }
+                    e->ops.push_back(Op{OP_CONV_TC_TF32, i, [plan](cudaStream_t s) { tc_launch(plan, s); }});
+                } else if (use_tc[i]) {
                     const bool fuse_yolo = opt.fuse && fused_into[i] < 0 && odt == DT_F32 && i + 1 < nl &&
                                            net->layers[i + 1].type == YB_YOLO && cons[i].size() == 1 && cons[i][0] == i + 1 &&
                                            e->d_final[i + 1] && !getenv("YB_NO_YOLO_FUSE");

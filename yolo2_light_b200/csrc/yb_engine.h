@@ -15,7 +15,8 @@ namespace yb {
 enum OpKind {
     OP_INPUT = 0, OP_CONV_SIMT = 1, OP_CONV_TC = 2, OP_BINARIZE = 3, OP_CONV_XNOR = 4, OP_QUANTIZE = 5,
     OP_CONV_INT8 = 6, OP_MAXPOOL = 7, OP_UPSAMPLE = 8, OP_SHORTCUT = 9, OP_ROUTE_COPY = 10, OP_REORG = 11,
-    OP_YOLO = 12, OP_REGION = 13, OP_CONV_TC_I8 = 14, OP_CONV_TC2 = 15   // k_conv_tc<2>: CTA pairs (cta_group::2)
+    OP_YOLO = 12, OP_REGION = 13, OP_CONV_TC_I8 = 14, OP_CONV_TC2 = 15,  // k_conv_tc<2>: CTA pairs (cta_group::2)
+    OP_CONV_TC_TF32 = 16
 };
 
 struct EngineOptions {
