@@ -353,3 +353,29 @@ def test_int8_calibration_on_device(name, workdir):
     # the engine is back in its normal (fused) configuration and still right
     net.set_option("fuse", 1)
     net.predict(x)
+
+
+@pytest.mark.parametrize("name,q", [("tiny64", 1), ("xnor64", 0), ("tinyvoc64", 1), ("tiny_w96_h64", 1)])
+def test_maxpool_fused_with_quantise_or_binarise_is_bit_exact(name, q, workdir):
+    """fuse=1 lets a max-pool write the s8 / sign input of the integer convolution that follows (k_maxpool_fused):
+    the same values in the same order as max-pool + quantise / binarise, so everything downstream is bit-identical."""
+    import yolo2_light_b200 as yb
+    B = 3
+    x = util.images(name, B)
+    res = []
+    for fuse in (0, 1):
+        net = _load(name, workdir, B, q, precision=yb.YB_PREC_FP32)
+        net.set_option("fuse", fuse)
+        net.set_option("keep_counts", 1)
+        net.predict(x, quantized=bool(q))
+        kinds = [k for _, k, _ in net.profile(quantized=bool(q))]
+        ints = [i for i, l in enumerate(net.layers)
+                if l["type_name"] == "CONVOLUTIONAL" and (l["xnor"] or (q and i >= 1 and l["activation"] != 3))]
+        res.append((kinds, {i: o.copy() for i, o in net.detection_outputs().items()},
+                    [net.fetch_counts(i, quantized=bool(q)) for i in ints]))
+    k0, k1 = res[0][0], res[1][0]
+    assert (k1.count("quantize") + k1.count("binarize")) < (k0.count("quantize") + k0.count("binarize")), (k0, k1)
+    for i in res[0][1]:
+        assert np.array_equal(res[0][1][i], res[1][1][i]), (name, i)
+    for a, b in zip(res[0][2], res[1][2]):
+        assert np.array_equal(a, b)

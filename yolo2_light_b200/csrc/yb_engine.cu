@@ -69,6 +69,7 @@ struct Engine {
     std::vector<int32_t *> d_counts;   // optional raw integer results per conv layer
     std::vector<size_t> counts_count;
     std::vector<Op> ops;
+    std::vector<char> not_materialised;   // layer outputs that exist only in a consumer's fused form
     TV in0{};
     int in0_dt = DT_F32;
     cudaGraphExec_t graph_exec = nullptr;
@@ -384,6 +385,8 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
     std::vector<char> hostw;
     auto reserve = [&](size_t bytes) { size_t off = align_up(hostw.size(), 1024); hostw.resize(off + bytes, 0); return off; };
     std::vector<int> use_tc(nl, 0);
+    e->not_materialised.assign(nl, 0);
+    std::vector<char> prefilled(nl, 0);   // the producing max-pool already wrote this conv's s8 / sign input (fused)
     for (int i = 0; i < nl; ++i) {
         const Layer &l = net->layers[i];
         if (l.type != YB_CONVOLUTIONAL) continue;
@@ -647,7 +650,8 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                     TV q = make_tv(e->act_arena + side_off[i], B, l.h, l.w, l.c, l.c, P, DT_S8, 0);
                     if (tc_i8_supported(l, q, tout)) {
                         const int g = grid_for((long)B * l.h * l.w * (l.c / 16));
-                        e->ops.push_back(Op{OP_BINARIZE, i, [tin, q, g](cudaStream_t s) { k_binarize_s8<<<g, 256, 0, s>>>(tin, q); }});
+                        if (!prefilled[i])
+                            e->ops.push_back(Op{OP_BINARIZE, i, [tin, q, g](cudaStream_t s) { k_binarize_s8<<<g, 256, 0, s>>>(tin, q); }});
                         void *plan = tc_make_plan_xnor(l, q, tout, e->w_arena + cw[i].w_s8, cw[i].ldn,
                                                        reinterpret_cast<const float *>(e->w_arena + cw[i].bias),
                                                        reinterpret_cast<const float *>(e->w_arena + cw[i].mean), cnt_dbg);
@@ -662,11 +666,13 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                 {
                     if (in_vec) {
                         const int g = grid_for((long)B * l.h * l.w * CW);
-                        e->ops.push_back(Op{OP_BINARIZE, i, [tin, bits, g](cudaStream_t s) { k_binarize_vec<float><<<g, 256, 0, s>>>(tin, bits); }});
+                        if (!prefilled[i])
+                            e->ops.push_back(Op{OP_BINARIZE, i, [tin, bits, g](cudaStream_t s) { k_binarize_vec<float><<<g, 256, 0, s>>>(tin, bits); }});
                     } else {
                         const long total = (long)B * l.h * l.w * CW * 32;
                         const int g = grid_for(total);
-                        e->ops.push_back(Op{OP_BINARIZE, i, [tin, bits, g](cudaStream_t s) { k_binarize<float><<<g, 256, 0, s>>>(tin, bits); }});
+                        if (!prefilled[i])
+                            e->ops.push_back(Op{OP_BINARIZE, i, [tin, bits, g](cudaStream_t s) { k_binarize<float><<<g, 256, 0, s>>>(tin, bits); }});
                     }
                 }
                 XnorP p{};
@@ -698,7 +704,8 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                 {
                     const long total = (long)B * l.h * l.w * (cpad / 4);
                     const int g = grid_for(total);
-                    e->ops.push_back(Op{OP_QUANTIZE, i, [tin, q, mult, g](cudaStream_t s) { k_quantize<float><<<g, 256, 0, s>>>(tin, q, mult); }});
+                    if (!prefilled[i])
+                        e->ops.push_back(Op{OP_QUANTIZE, i, [tin, q, mult, g](cudaStream_t s) { k_quantize<float><<<g, 256, 0, s>>>(tin, q, mult); }});
                 }
                 int *acc_dbg = nullptr;
                 if (opt.keep_counts) {
@@ -731,6 +738,35 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
             need_prev();
             const TV tout = e->out_tv[i];
             const int size = l.size, stride = l.stride, pad = l.pad;
+            // max-pool -> integer convolution: write the convolution's s8 / sign input directly (same values in the same
+            // order as max-pool + quantise / binarise; the pooled f32 tensor never goes to HBM)
+            if (opt.fuse && in_dt == DT_F32 && i + 1 < nl && cons[i].size() == 1 && cons[i][0] == i + 1 &&
+                net->layers[i + 1].type == YB_CONVOLUTIONAL && conv_variant(i + 1) != 0 && side_off[i + 1] != (size_t)-1 &&
+                !getenv("YB_NO_POOL_FUSE")) {
+                const Layer &c = net->layers[i + 1];
+                const int v = conv_variant(i + 1);
+                if (v == 2) {
+                    TV q = make_tv(e->act_arena + side_off[i + 1], B, c.h, c.w, c.c, side_ld[i + 1], P, DT_S8, 0);
+                    const float mult = c.input_quant_multipler;
+                    const int g = grid_for((long)B * c.h * c.w * (q.ldc / 4));
+                    e->ops.push_back(Op{OP_MAXPOOL, i, [tin, q, size, stride, pad, mult, g](cudaStream_t s) {
+                        k_maxpool_fused<0><<<g, 256, 0, s>>>(tin, q, size, stride, pad, mult); }});
+                } else if (xnor_on_tc(c)) {
+                    TV q = make_tv(e->act_arena + side_off[i + 1], B, c.h, c.w, c.c, c.c, P, DT_S8, 0);
+                    const int g = grid_for((long)B * c.h * c.w * (c.c / 4));
+                    e->ops.push_back(Op{OP_MAXPOOL, i, [tin, q, size, stride, pad, g](cudaStream_t s) {
+                        k_maxpool_fused<1><<<g, 256, 0, s>>>(tin, q, size, stride, pad, 0.f); }});
+                } else {
+                    const int CW = side_ld[i + 1];
+                    TV bits = make_tv(e->act_arena + side_off[i + 1], B, c.h, c.w, CW, CW, P, DT_BITS, 0);
+                    const int g = grid_for((long)B * c.h * c.w * CW);
+                    e->ops.push_back(Op{OP_MAXPOOL, i, [tin, bits, size, stride, pad, g](cudaStream_t s) {
+                        k_maxpool_fused<2><<<g, 256, 0, s>>>(tin, bits, size, stride, pad, 0.f); }});
+                }
+                prefilled[i + 1] = 1;
+                e->not_materialised[i] = 1;      // fetch_layer reports it
+                break;
+            }
             const int g = grid_for((long)B * l.out_h * l.out_w * l.out_c);
             const int dt = in_dt;
             const int esz = (int)dt_size(dt);
@@ -1019,8 +1055,8 @@ void engine_fetch_layer(Engine *e, Network *net, int layer, float *dst) {
         CUDA_OK(cudaMemcpy(dst, e->d_final[layer], count * sizeof(float), cudaMemcpyDeviceToHost));
         return;
     }
-    const TV t = e->out_tv[layer];
-    if (!t.base) fatal_throw("fetch_layer: layer " + std::to_string(layer) + " has no materialised output "
+ const TV t = e->out_tv[layer];
+    if (!t.base || e->not_materialised[layer]) fatal_throw("fetch_layer: layer " + std::to_string(layer) + " has no materialised output "
                              "(fused or aliased away; build the engine with fusion off)");
     float *tmp = nullptr;
     CUDA_OK(cudaMalloc(&tmp, count * sizeof(float)));
@@ -1061,7 +1097,7 @@ void engine_input_histogram(Engine *e, Network *net, int layer, int img, float b
         k_abs_hist_flat<<<grid_for(n), 256, 0, e->stream>>>(e->d_input + (size_t)img * n, n, bin_width, max_bin, d_hist);
     } else {
         const TV t = e->out_tv[layer - 1];
-        if (!t.base) { cudaFree(d_hist); fatal_throw("calibrate: the input of layer " + std::to_string(layer) +
+        if (!t.base || e->not_materialised[layer - 1]) { cudaFree(d_hist); fatal_throw("calibrate: the input of layer " + std::to_string(layer) +
                                                      " is not materialised (fused away; set option fuse=0)"); }
         const long n = (long)t.C * t.H * t.W;
         if (e->out_dt[layer - 1] == DT_F32) k_abs_hist<float><<<grid_for(n), 256, 0, e->stream>>>(t, img, bin_width, max_bin, d_hist);

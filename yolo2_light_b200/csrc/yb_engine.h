@@ -27,7 +27,7 @@ struct EngineOptions {
     bool upload = true;        // upload the weight arena (false on non-root ranks before the broadcast)
     int q_index_offset = 0;    // added to the layer index in the `i >= 1` INT8 rule (single-layer runs)
     bool keep_counts = false;  // keep raw XNOR popcounts / INT8 accumulators (tests)
-    bool ksplit = true;        // K-split of the tail wave of the tensor-core convolutions
+    bool ksplit = false;       // K-split of the tail wave of the tensor-core convolutions (opt-in, see yb_model.h)
 };
 
 struct Engine;

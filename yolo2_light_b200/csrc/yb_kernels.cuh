@@ -728,6 +728,69 @@ __global__ void k_maxpool_vec(TV in, TV out, int size, int stride, int pad) {
     }
 }
 
+// max-pool fused with the consumer's input transform (exact: same values, same operation order as max-pool followed by
+// k_quantize / k_binarize_s8 / k_binarize_vec -- the f32 pooled tensor just never goes to HBM).
+//   MODE 0: s8 = quant_i8(max, mult)          -> q (s8, ldc % 4 == 0, zero channel padding)   [INT8 convolutions]
+//   MODE 1: s8 = max > 0 ? +1 : -1            -> q (s8, ldc == C, C % 4 == 0)                 [XNOR on kind::i8]
+//   MODE 2: bit = max > 0, 32 channels / word -> bits (ldc words)                              [XNOR popcount kernels]
+template <int MODE>
+__global__ void k_maxpool_fused(TV in /* f32 */, TV q, int size, int stride, int pad, float mult) {
+    const int groups = (MODE == 2) ? q.ldc : (q.ldc >> 2);      // output words per pixel
+    const int OH = q.H, OW = q.W;
+    const long total = (long)q.N * OH * OW * groups;
+    const int off = -pad / 2;
+    constexpr int V = (MODE == 2) ? 32 : 4;                      // channels per output word
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % groups);
+        const long pxl = i / groups;
+        const int x = (int)(pxl % OW);
+        const int y = (int)((pxl / OW) % OH);
+        const int n = (int)(pxl / ((long)OW * OH));
+        float m[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) m[k] = -3.402823466e+38f;
+        for (int a = 0; a < size; ++a) {
+            const int iy = off + y * stride + a;
+            if (iy < 0 || iy >= in.H) continue;
+            for (int b = 0; b < size; ++b) {
+                const int ix = off + x * stride + b;
+                if (ix < 0 || ix >= in.W) continue;
+                const float *src = tv_px<float>(in, n, iy, ix) + g * V;
+#pragma unroll
+                for (int k = 0; k < V; k += 4) {
+                    if (g * V + k + 3 < in.C) {
+                        const float4 v = __ldg(reinterpret_cast<const float4 *>(src + k));
+                        m[k] = v.x > m[k] ? v.x : m[k]; m[k + 1] = v.y > m[k + 1] ? v.y : m[k + 1];
+                        m[k + 2] = v.z > m[k + 2] ? v.z : m[k + 2]; m[k + 3] = v.w > m[k + 3] ? v.w : m[k + 3];
+                    } else {
+                        for (int j = 0; j < 4; ++j)
+                            if (g * V + k + j < in.C) { const float f = __ldg(src + k + j); m[k + j] = f > m[k + j] ? f : m[k + j]; }
+                    }
+                }
+            }
+        }
+        uint32_t word = 0;
+        if (MODE == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = g * 4 + j;
+                const int s = (c < in.C) ? quant_i8(m[j], mult) : 0;
+                word |= (uint32_t)(s & 0xff) << (8 * j);
+            }
+            reinterpret_cast<uint32_t *>(tv_px<int8_t>(q, n, y, x))[g] = word;
+        } else if (MODE == 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) word |= (uint32_t)((m[j] > 0.f ? 1 : -1) & 0xff) << (8 * j);
+            reinterpret_cast<uint32_t *>(tv_px<int8_t>(q, n, y, x))[g] = word;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (g * 32 + j < in.C && m[j] > 0.f) word |= 1u << j;
+            tv_px<uint32_t>(q, n, y, x)[g] = word;
+        }
+    }
+}
+
 // upsample_cpu forward (reference yolov2_forward_network.c:380-394): out = scale * in[y/stride][x/stride]
 template <typename T>
 __global__ void k_upsample(TV in, TV out, int stride, float scale) {
