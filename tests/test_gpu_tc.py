@@ -179,10 +179,12 @@ def test_tc_ksplit_tail_matches_plain_schedule(h, w, batch, workdir):
         # identical bf16 inputs per layer only if the previous layer agreed bit for bit; the drift of a few bf16 ulps
         # accumulates down the (unfused, layer by layer) chain
         assert util.rel_l2(b, a) <= 4e-3, (i, util.rel_l2(b, a))
-    # fused engine, CUDA graph replays
+    # fused engine, CUDA graph replays; the split is opt-in
     net = yb.load_network(cfg, wts, batch=batch)
+    assert net.get_info("ksplit_layers") == 0
+    net.set_option("ksplit", 1)
+    assert net.get_info("ksplit_layers") >= 3
     ref = yb.load_network(cfg, wts, batch=batch)
-    ref.set_option("ksplit", 0)
     for rep in range(3):
         net.predict(x); ref.predict(x)
     for i, o in net.detection_outputs().items():
