@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "yb_conv_tc.cuh"
@@ -417,10 +418,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
     } else if (warp == 1) {
         // ======================= MMA issuer (CG=2: the leader CTA only, for both CTAs) =======================
-        if (leader && elect_one()) {
+        // the operand kind is fixed per launch: one copy of the issue loop per kind, chosen once -- a per-MMA branch on it
+        // costs the single issuing thread ~2 % of the whole yolov3 step (the BN <= 128 layers are issue-bound)
+        auto mma_role = [&](auto kind_c) {
+            constexpr int KIND = decltype(kind_c)::value;
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            const int kk = p.kk, kind = p.kind, sps = p.sps, kblocks = p.kblocks, stages = p.stages, BN = p.BN;
+            const int kk = p.kk, sps = p.sps, kblocks = p.kblocks, stages = p.stages, BN = p.BN;
             const uint32_t a_bytes = p.a_bytes, b_bytes = p.b_bytes, stage_bytes = p.stage_bytes, idesc = p.idesc, dbg = (uint32_t)p.dbg;
             const uint32_t b_off = (uint32_t)sps * a_bytes;
             const uint64_t hi = (uint64_t)p.desc_hi << 32;
@@ -449,8 +453,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         const int first = (kb0 - kb_begin) | j;     // 0 on the first K-block of the segment: overwrite the accumulator
                         for (int k = 0; k < kk; ++k) {
                             if constexpr (CG == 2) umma2_bf16(d_tmem, adesc, bdesc, idesc, (uint32_t)((first | k) != 0));
-                            else if (kind == 3) umma_tf32(d_tmem, adesc, bdesc, idesc, (uint32_t)((first | k) != 0));
-                            else if (kind != 0) umma_i8(d_tmem, adesc, bdesc, idesc, (uint32_t)((first | k) != 0));
+                            else if constexpr (KIND == 3) umma_tf32(d_tmem, adesc, bdesc, idesc, (uint32_t)((first | k) != 0));
+                            else if constexpr (KIND == 1) umma_i8(d_tmem, adesc, bdesc, idesc, (uint32_t)((first | k) != 0));
                             else umma_bf16(d_tmem, adesc, bdesc, idesc, (uint32_t)((first | k) != 0));
                             adesc += 2; bdesc += 2;
                         }
@@ -465,6 +469,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
             if (p.stats) { p.stats[blockIdx.x * 8 + 2] = (unsigned long long)w_full; p.stats[blockIdx.x * 8 + 3] = (unsigned long long)w_tempty;
                            p.stats[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_begin); }
+        };
+        if (leader && elect_one()) {
+            if constexpr (CG == 2) mma_role(std::integral_constant<int, 0>{});
+            else if (p.kind == 0) mma_role(std::integral_constant<int, 0>{});
+            else if (p.kind == 3) mma_role(std::integral_constant<int, 3>{});
+            else mma_role(std::integral_constant<int, 1>{});
         }
     } else {
         // ======================= epilogue (warps 2..9) =======================
@@ -1292,7 +1302,7 @@ size_t tc_ksplit_flag_bytes(int sms) { return (size_t)sms * TC_EPI_WARPS * sizeo
 int tc_plan_enable_ksplit(void *vp, float *ws, unsigned *flags) {
     TcPlan *plan = reinterpret_cast<TcPlan *>(vp);
     TcParams &p = plan->p;
-    const char *ev = getenv("YB_TC_KSPLIT");
+    const char *ev = getenv("YB_TC_KSPLIT");                 // 0: never (even when the option asks for it)
     if (ev && ev[0] == '0') return 0;
     if (p.kind != 0 || !ws || !flags) return 0;
     int dev = 0, sms = 148;

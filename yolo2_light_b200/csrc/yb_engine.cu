@@ -609,7 +609,9 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                         CUDA_OK(cudaMemset(e->ksplit_flags, 0, tc_ksplit_flag_bytes(sms)));
                     }
                     ++e->n_tc;
-                    if (opt.ksplit) e->n_ksplit += tc_plan_enable_ksplit(plan, e->ksplit_ws, e->ksplit_flags);
+                    const char *ks_env = getenv("YB_TC_KSPLIT");   // 1: on without the option (A/B runs)
+                    if (opt.ksplit || (ks_env && ks_env[0] == '1'))
+                        e->n_ksplit += tc_plan_enable_ksplit(plan, e->ksplit_ws, e->ksplit_flags);
                     if (fuse_yolo) {
                         tc_plan_fuse_yolo(plan, e->d_final[i + 1], net->layers[i + 1].classes);
                         yolo_fused[i + 1] = 1;
