@@ -14,7 +14,8 @@ scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 kn = hdr.index("Kernel Name")
 tot, ids = 0.0, set()
 for r in rows[hi + 1:]:
-    if len(r) <= mv or not r[mn].startswith("dram__bytes") or "k_conv_tc<2>" not in r[kn].replace("(int)2", "2"):
+    nm = r[kn].replace("(int)", "").replace("(bool)", "").replace(" ", "") if len(r) > kn else ""
+    if len(r) <= mv or not r[mn].startswith("dram__bytes") or "k_conv_tc<2" not in nm:
         continue
     tot += float(r[mv].replace(",", "")) * scale.get(r[mu], 1); ids.add(r[idc])
 out = {"yolov3-608-fp32-b16": {"dram_bytes_per_launch": tot / max(len(ids), 1), "launches": len(ids), "total_bytes": tot,
