@@ -1143,7 +1143,8 @@ int engine_detect(Engine *e, Network *net, int w, int h, float thresh, float nms
     }
     P.thresh = thresh; P.nms = nms; P.max_rows = max_rows; P.nblk = (total + 255) / 256;
     const int B = e->batch, stride = 5 + P.classes, words = (max_rows + 31) / 32;
-    if (e->det_cap < max_rows || e->det_stride != stride || e->det_nblk < P.nblk) {
+    if (e->det_cap != max_rows || e->det_stride != stride || e->det_nblk < P.nblk) {   // pitch == cap == max_rows: the NMS
+                                                                                           // sees exactly the rows the caller asked for
         if (e->det_rows) cudaFree(e->det_rows);
         if (e->det_mask) cudaFree(e->det_mask);
         if (e->det_blkcnt) cudaFree(e->det_blkcnt);
