@@ -13,8 +13,12 @@
 //   * One elected thread issues tcgen05.mma (kind::f16, bf16 x bf16 -> f32, M=128, N=BN<=256, K=16) with the
 //     accumulator in TMEM; tcgen05.commit releases shared-memory stages / publishes the accumulator through
 //     mbarriers.  Two TMEM accumulators let the epilogue of tile i overlap the main loop of tile i+1.
-//   * 4 epilogue warps read TMEM (tcgen05.ld 32x32b.x32), add bias (folded batch-norm), apply leaky-ReLU, add the
-//     shortcut residual when fused (reference :443-449), and store bf16 (or f32 for detection heads) NHWC.
+//   * 8 epilogue warps read TMEM (tcgen05.ld 32x32b.x32), add bias (folded batch-norm), apply leaky-ReLU, add the
+//     shortcut residual when fused (reference :443-449), and store bf16 NHWC through a swizzled staging tile (whole
+//     128-byte lines), or f32 for detection heads -- optionally with the following [yolo] layer applied (:453-472).
+//   * The same kernel runs the INT8 variant (kind::i8, exact requantising epilogue, yolov2_forward_network_quantized.c:
+//     474-490), wide XNOR layers as +-1 bytes on kind::i8, and the float heads of the exact networks on kind::tf32.
+//   * CG = 2: CTA pairs (cta_group::2) for the BN = 256 layers; KS = true: K-split of the tail wave (opt-in).
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue
 // (two warps per TMEM lane quarter, each owning half of the accumulator columns).
