@@ -239,6 +239,18 @@ float yb_entropy_calibration(const float *src, size_t size, float bin_width, int
 int yb_network_input_histogram(yb_network *net, int quantized, int layer, int img, float bin_width, int max_bin,
                                uint32_t *hist);
 
+/* ---- mAP accounting ------------------------------------------------------------------ */
+
+/* The bookkeeping of validate_detector_map (src/additionally.c:4541-4898) on detections produced elsewhere: `rows` =
+ * the concatenated rows of all images ({x, y, w, h, objectness, prob[classes]}, relative coordinates; what
+ * yb_network_detect / yb_get_network_boxes return for w = h = 1, thresh .005, nms .45 as the reference uses),
+ * rows_per_image[nimages]; truth[ntruth][6] = {image, class, x, y, w, h} (the label files' content, in file order).
+ * Outputs: ap_per_class[classes] (11-point interpolated AP, :4848), *map_out, stats[8] = {precision, recall, F1,
+ * average IoU, TP, FP, FN at thresh_calc_avg_iou (:4872-4880), number of detections}.  Returns the number of
+ * (box, class) detections ranked, or -1.  The "difficult" list is not modelled. */
+int yb_map_evaluate(const float *rows, const int *rows_per_image, int nimages, int classes, const float *truth, int ntruth,
+                    float iou_thresh, float thresh_calc_avg_iou, double *ap_per_class, double *map_out, float *stats);
+
 const char *yb_version(void);
 
 #ifdef __cplusplus

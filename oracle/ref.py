@@ -143,6 +143,17 @@ class RefNet:
         return out[:min(n, max_out)]
 
 
+def validate_map(datacfg: str, cfg: str, weights: str, thresh_calc_avg_iou: float, quantized: int, iou_thresh: float,
+                 out_path: str, kind: str = "scalar") -> str:
+    """Runs the reference's validate_detector_map and returns what it printed."""
+    lib = _load(kind)
+    lib.refh_validate_map.restype = None
+    lib.refh_validate_map.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_float, C.c_int, C.c_float, C.c_char_p]
+    lib.refh_validate_map(datacfg.encode(), cfg.encode(), weights.encode(), thresh_calc_avg_iou, quantized, iou_thresh,
+                          out_path.encode())
+    return open(out_path).read()
+
+
 def entropy_calibration(src: np.ndarray, bin_width: float = 1.0 / 16, max_bin: int = 4096, kind: str = "scalar") -> float:
     """The reference's entropy_calibration on one float array (prints one line to stdout, like the reference)."""
     lib = _load(kind)

@@ -231,6 +231,25 @@ float refh_entropy_calibration(float *src, long size, float bin_width, int max_b
     return entropy_calibration(src, (size_t)size, bin_width, max_bin);
 }
 
+/* mAP driver of the reference: validate_detector_map, additionally.c:4541-4898, with its stdout (the only
+ * place the numbers go) redirected into `out_path`. */
+void validate_detector_map(char *datacfg, char *cfgfile, char *weightfile, float thresh_calc_avg_iou, int quantized,
+                           const float iou_thresh);
+void refh_validate_map(const char *datacfg, const char *cfg, const char *weights, float thresh_calc_avg_iou, int quantized,
+                       float iou_thresh, const char *out_path)
+{
+    fflush(stdout);
+    int saved = dup(1);
+    FILE *f = fopen(out_path, "w");
+    if (!f) return;
+    dup2(fileno(f), 1);
+    validate_detector_map((char *)datacfg, (char *)cfg, (char *)weights, thresh_calc_avg_iou, quantized, iou_thresh);
+    fflush(stdout);
+    dup2(saved, 1);
+    close(saved);
+    fclose(f);
+}
+
 /* Image pipeline of the reference app: u8 HWC (what stbi_load returns) -> planar float /255. (load_image_stb,
  * additionally.c:3080-3103) -> resize_image bilinear to the network size (additionally.c:3021-3064, only when the
  * size differs, load_image :3066-3078).  out: float[c*out_h*out_w]. */

@@ -92,6 +92,7 @@ def lib():
         "yb_network_calibrate": (C.c_int, [vp, vp, vp, C.c_int]),
         "yb_entropy_calibration": (C.c_float, [vp, C.c_size_t, C.c_float, C.c_int]),
         "yb_network_input_histogram": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp]),
+        "yb_map_evaluate": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_float, C.c_float, vp, vp, vp]),
         "yb_network_detect": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, vp, C.c_int, vp]),
         "yb_network_predict": (fp, [vp, vp]),
         "yb_network_predict_quantized": (fp, [vp, vp]),
@@ -131,7 +132,7 @@ EXPORTED_SYMBOLS = [
     "yb_network_from_layers", "yb_free_network", "yb_network_num_layers", "yb_network_dims", "yb_network_layer",
     "yb_network_layer_outputs", "yb_network_input_calibration", "yb_set_batch_network", "yb_network_set_device",
     "yb_network_set_precision", "yb_network_set_option", "yb_network_get_info", "yb_network_detect", "yb_network_calibrate", "yb_entropy_calibration",
-    "yb_network_input_histogram", "yb_network_predict", "yb_network_predict_quantized",
+    "yb_network_input_histogram", "yb_map_evaluate", "yb_network_predict", "yb_network_predict_quantized",
     "yb_network_predict_image_u8", "yb_network_fetch_input", "yb_network_submit", "yb_network_collect", "yb_network_layer_output", "yb_network_forward_device", "yb_network_sync_outputs", "yb_network_fetch_layer",
     "yb_network_fetch_counts", "yb_forward_convolutional_layer", "yb_network_weight_arena",
     "yb_network_last_launches", "yb_network_profile", "yb_op_kind_name", "yb_get_network_boxes", "yb_alloc_pinned",
@@ -383,6 +384,23 @@ class Network:
                                     rows.ctypes.data_as(C.c_void_p), max_rows, counts.ctypes.data_as(C.c_void_p))
         _check(r == 5 + classes)
         return [rows[b, :min(int(counts[b]), max_rows)] for b in range(self.batch)], counts
+
+
+def map_evaluate(rows_per_image_list, truth: np.ndarray, classes: int, iou_thresh: float = 0.5,
+                 thresh_calc_avg_iou: float = 0.24):
+    """``yb_map_evaluate``: rows_per_image_list = one [n_i, 5 + classes] array per image (relative coordinates),
+    truth = float32 [ntruth, 6] {image, class, x, y, w, h}.  Returns (mAP, ap_per_class, stats dict)."""
+    rows = [np.ascontiguousarray(r, np.float32).reshape(-1, 5 + classes) for r in rows_per_image_list]
+    counts = np.array([r.shape[0] for r in rows], np.int32)
+    flat = np.ascontiguousarray(np.concatenate(rows, 0) if rows else np.zeros((0, 5 + classes), np.float32))
+    t = np.ascontiguousarray(truth, np.float32).reshape(-1, 6)
+    ap = np.zeros(classes, np.float64); m = C.c_double(0); st = np.zeros(8, np.float32)
+    r = lib().yb_map_evaluate(flat.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p), len(rows), classes,
+                              t.ctypes.data_as(C.c_void_p), t.shape[0], iou_thresh, thresh_calc_avg_iou,
+                              ap.ctypes.data_as(C.c_void_p), C.byref(m), st.ctypes.data_as(C.c_void_p))
+    _check(r >= 0)
+    keys = ("precision", "recall", "f1", "avg_iou", "tp", "fp", "fn", "detections")
+    return float(m.value), ap, dict(zip(keys, (float(v) for v in st)))
 
 
 def entropy_calibration(src: np.ndarray, bin_width: float = 1.0 / 16, max_bin: int = 4096) -> float:

@@ -409,6 +409,14 @@ int yb_network_input_histogram(yb_network *n, int quantized, int layer, int img,
     YB_CATCH(-1)
 }
 
+int yb_map_evaluate(const float *rows, const int *rows_per_image, int nimages, int classes, const float *truth, int ntruth,
+                    float iou_thresh, float thresh_calc_avg_iou, double *ap_per_class, double *map_out, float *stats) {
+    YB_TRY
+    return map_evaluate(rows, rows_per_image, nimages, classes, truth, ntruth, iou_thresh, thresh_calc_avg_iou,
+                        ap_per_class, map_out, stats);
+    YB_CATCH(-1)
+}
+
 /* pinned host memory for the end-to-end path (input images) */
 void *yb_alloc_pinned(size_t bytes);
 void yb_free_pinned(void *p);

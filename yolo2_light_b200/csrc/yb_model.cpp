@@ -618,4 +618,117 @@ void abs_histogram_host(const float *src, size_t n, float bin_width, int max_bin
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// mAP accounting: the bookkeeping of validate_detector_map, additionally.c:4541-4898, on detection
+// rows produced elsewhere (yb_network_detect / yb_get_network_boxes with w = h = 1, thresh .005, nms .45 as the
+// reference uses, :4576-4577, :4657-4659).  Same matching rule (best IoU above iou_thresh with equal class, :4711-4722),
+// same global ranking by confidence (:4784), same 11-point interpolated AP (:4848-4866), same precision / recall / F1 /
+// average-IoU figures at thresh_calc_avg_iou (:4745-4760, :4872-4880).  The "difficult" list (:4724-4735) is not modelled.
+// ------------------------------------------------------------------------------------------------------
+namespace {
+struct BoxProb { float x, y, w, h, p; int class_id, image_index, truth_flag, unique_truth_index; };
+float iou_xywh(float ax, float ay, float aw, float ah, float bx, float by, float bw, float bh) {
+    Det a, b;
+    a.x = ax; a.y = ay; a.w = aw; a.h = ah; b.x = bx; b.y = by; b.w = bw; b.h = bh;
+    return box_iou(a, b);
+}
+}  // namespace
+
+int map_evaluate(const float *rows, const int *rows_per_image, int nimages, int classes, const float *truth /* [n][6]:
+                 image, class, x, y, w, h */, int ntruth, float iou_thresh, float thresh_calc_avg_iou,
+                 double *ap_per_class, double *map_out, float *stats /* precision, recall, f1, avg_iou, tp, fp, fn, ndet */) {
+    const int stride = 5 + classes;
+    std::vector<BoxProb> det;
+    std::vector<int> truth_classes_count(classes, 0);
+    int unique_truth_count = 0, tp_for_thresh = 0, fp_for_thresh = 0;
+    float avg_iou = 0;
+    // truths grouped per image, in file order
+    std::vector<std::vector<const float *>> per_image(nimages);
+    for (int j = 0; j < ntruth; ++j) {
+        const int im = (int)truth[(size_t)j * 6];
+        if (im < 0 || im >= nimages) fatal_throw("map_evaluate: truth image index out of range");
+        const int id = (int)truth[(size_t)j * 6 + 1];
+        if (id < 0 || id >= classes) fatal_throw("map_evaluate: truth class out of range");
+        per_image[im].push_back(truth + (size_t)j * 6);
+    }
+    const float *r = rows;
+    for (int image_index = 0; image_index < nimages; ++image_index) {
+        const auto &tr = per_image[image_index];
+        const int num_labels = (int)tr.size();
+        for (const float *t : tr) truth_classes_count[(int)t[1]]++;
+        const size_t checkpoint = det.size();
+        for (int i = 0; i < rows_per_image[image_index]; ++i, r += stride) {
+            for (int class_id = 0; class_id < classes; ++class_id) {
+                const float prob = r[5 + class_id];
+                if (!(prob > 0)) continue;
+                BoxProb d{r[0], r[1], r[2], r[3], prob, class_id, image_index, 0, -1};
+                int truth_index = -1;
+                float max_iou = 0;
+                for (int j = 0; j < num_labels; ++j) {
+                    const float *t = tr[j];
+                    const float cur = iou_xywh(r[0], r[1], r[2], r[3], t[2], t[3], t[4], t[5]);
+                    if (cur > iou_thresh && class_id == (int)t[1] && cur > max_iou) { max_iou = cur; truth_index = unique_truth_count + j; }
+                }
+                if (truth_index > -1) { d.truth_flag = 1; d.unique_truth_index = truth_index; }
+                det.push_back(d);
+                if (prob > thresh_calc_avg_iou) {
+                    bool found = false;
+                    for (size_t z = checkpoint; z + 1 < det.size(); ++z)
+                        if (det[z].unique_truth_index == truth_index) { found = true; break; }
+                    if (truth_index > -1 && !found) { avg_iou += max_iou; ++tp_for_thresh; }
+                    else ++fp_for_thresh;
+                }
+            }
+        }
+        unique_truth_count += num_labels;
+    }
+    if (tp_for_thresh + fp_for_thresh > 0) avg_iou = avg_iou / (tp_for_thresh + fp_for_thresh);
+    // SORT(detections): descending confidence (qsort's tie order is unspecified; ties keep insertion order here)
+    std::stable_sort(det.begin(), det.end(), [](const BoxProb &a, const BoxProb &b) { return (a.p - b.p) > 0; });
+    const int n = (int)det.size();
+    struct PR { double precision, recall; int tp, fp; };
+    std::vector<std::vector<PR>> pr(classes, std::vector<PR>(std::max(n, 1), PR{0, 0, 0, 0}));
+    std::vector<char> truth_flags(std::max(unique_truth_count, 1), 0);
+    for (int rank = 0; rank < n; ++rank) {
+        if (rank > 0)
+            for (int c = 0; c < classes; ++c) { pr[c][rank].tp = pr[c][rank - 1].tp; pr[c][rank].fp = pr[c][rank - 1].fp; }
+        const BoxProb &d = det[rank];
+        if (d.truth_flag == 1) {
+            if (!truth_flags[d.unique_truth_index]) { truth_flags[d.unique_truth_index] = 1; pr[d.class_id][rank].tp++; }
+        } else {
+            pr[d.class_id][rank].fp++;
+        }
+        for (int c = 0; c < classes; ++c) {
+            const int tp = pr[c][rank].tp, fp = pr[c][rank].fp, fn = truth_classes_count[c] - tp;
+            pr[c][rank].precision = (tp + fp) > 0 ? (double)tp / (double)(tp + fp) : 0;
+            pr[c][rank].recall = (tp + fn) > 0 ? (double)tp / (double)(tp + fn) : 0;
+        }
+    }
+    double mean_ap = 0;
+    for (int c = 0; c < classes; ++c) {
+        double avg_precision = 0;
+        for (int point = 0; point < 11; ++point) {
+            const double cur_recall = point * 0.1;
+            double cur_precision = 0;
+            for (int rank = 0; rank < n; ++rank)
+                if (pr[c][rank].recall >= cur_recall && pr[c][rank].precision > cur_precision) cur_precision = pr[c][rank].precision;
+            avg_precision += cur_precision;
+        }
+        avg_precision = avg_precision / 11;
+        if (ap_per_class) ap_per_class[c] = avg_precision;
+        mean_ap += avg_precision;
+    }
+    mean_ap = mean_ap / classes;
+    if (map_out) *map_out = mean_ap;
+    if (stats) {
+        const float cur_precision = (float)tp_for_thresh / ((float)tp_for_thresh + (float)fp_for_thresh);
+        const float cur_recall = (float)tp_for_thresh / ((float)tp_for_thresh + (float)(unique_truth_count - tp_for_thresh));
+        stats[0] = cur_precision; stats[1] = cur_recall;
+        stats[2] = 2.F * cur_precision * cur_recall / (cur_precision + cur_recall);
+        stats[3] = avg_iou; stats[4] = (float)tp_for_thresh; stats[5] = (float)fp_for_thresh;
+        stats[6] = (float)(unique_truth_count - tp_for_thresh); stats[7] = (float)n;
+    }
+    return n;
+}
+
 }  // namespace yb

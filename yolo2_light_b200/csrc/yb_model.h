@@ -68,6 +68,8 @@ void set_batch(Network *net, int batch);
 int get_boxes(const Network *net, int b, int w, int h, float thresh, float nms, int relative, int letter,
               float *out, int max_rows);
 
+int map_evaluate(const float *rows, const int *rows_per_image, int nimages, int classes, const float *truth, int ntruth,
+                 float iou_thresh, float thresh_calc_avg_iou, double *ap_per_class, double *map_out, float *stats);
 float entropy_from_histogram(const uint32_t *hist, float bin_width, int max_bin);
 void abs_histogram_host(const float *src, size_t n, float bin_width, int max_bin, uint32_t *hist);
 
