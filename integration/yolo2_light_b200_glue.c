@@ -7,6 +7,8 @@
  *
  *     float *network_predict_b200(network net, float *input);
  *     float *network_predict_b200_quantized(network net, float *input);
+ *     detection *get_network_boxes_nms_b200(network *net, int w, int h, float thresh, float nms, int relative, int *num,
+ *                                           int letter);      (optional: decode + NMS on the device)
  *
  * Call sites to switch: src/main.c:199-219, src/main.c:394-414, src/additionally.c:4639-4659.
  * Preconditions are the reference's own (main.c:160-171): parse_network_cfg, load_weights_upto_cpu,
@@ -86,6 +88,51 @@ static float *glue_predict(network net, float *input, int quantized)
     }
     for (i = net.n - 1; i > 0; --i) if (net.layers[i].type != COST) break;   /* as network_predict_cpu returns */
     return net.layers[i].output;
+}
+
+static yb_network *glue_find(network *net)
+{
+    int k;
+    for (k = 0; k < YB_GLUE_MAX_NETS; ++k)
+        if (g_nets[k].h && g_nets[k].key == net->layers) return g_nets[k].h;
+    return NULL;
+}
+
+/*
+ * Slot of the pair  dets = get_network_boxes(net, w, h, thresh, hier, map, relative, &n, letter);  do_nms_sort(dets, n,
+ * classes, nms);  (src/main.c:228-229, :423-427): decode + NMS run on the device, on the tensors the last
+ * network_predict_b200[_quantized](net, ...) left in HBM, and only the candidate rows come back.  Returns a `detection`
+ * array laid out like make_network_boxes' (src/additionally.c:4238: prob[classes] per entry), to be released with the
+ * reference's free_detections.  batch item 0, like the reference.  nms = 0 skips the suppression.
+ */
+detection *get_network_boxes_nms_b200(network *net, int w, int h, float thresh, float nms, int relative, int *num, int letter)
+{
+    yb_network *hnd = glue_find(net);
+    layer l = net->layers[net->n - 1];
+    const int classes = l.classes, stride = 5 + classes, cap = 8192;
+    float *rows;
+    int *counts, n, i, quantized = 0, k;
+    detection *dets;
+    if (!hnd) { fprintf(stderr, "get_network_boxes_nms_b200: call network_predict_b200 first\n"); exit(1); }
+    for (k = 0; k < YB_GLUE_MAX_NETS; ++k) if (g_nets[k].h == hnd) quantized = g_nets[k].quantized;
+    rows = (float *)malloc(sizeof(float) * (size_t)net->batch * cap * stride);
+    counts = (int *)calloc(net->batch, sizeof(int));
+    if (yb_network_detect(hnd, quantized, w, h, thresh, nms, relative, letter, rows, cap, counts) != stride) {
+        fprintf(stderr, "get_network_boxes_nms_b200: %s\n", yb_last_error()); exit(1);
+    }
+    n = counts[0] < cap ? counts[0] : cap;
+    dets = (detection *)calloc(n > 0 ? n : 1, sizeof(detection));
+    for (i = 0; i < n; ++i) {
+        const float *r = rows + (size_t)i * stride;
+        dets[i].bbox.x = r[0]; dets[i].bbox.y = r[1]; dets[i].bbox.w = r[2]; dets[i].bbox.h = r[3];
+        dets[i].objectness = r[4];
+        dets[i].classes = classes;
+        dets[i].prob = (float *)calloc(classes, sizeof(float));
+        memcpy(dets[i].prob, r + 5, sizeof(float) * classes);
+    }
+    if (num) *num = n;
+    free(rows); free(counts);
+    return dets;
 }
 
 float *network_predict_b200(network net, float *input) { return glue_predict(net, input, 0); }

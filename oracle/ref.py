@@ -135,6 +135,15 @@ class RefNet:
         x = np.ascontiguousarray(x, dtype=np.float32)
         return float(self.lib.refh_time_predict(self.h, x.ctypes.data_as(C.c_void_p), reps))
 
+    def get_boxes_b200(self, w: int, h: int, thresh: float, nms: float, max_out: int = 8192):
+        """get_network_boxes_nms_b200 of the glue (kind='dropin', after predict_b200): device-side decode + NMS."""
+        classes = self.layers[-1]["classes"]
+        out = np.zeros((max_out, 6 + classes), np.float32)
+        self.lib.refh_get_boxes_b200.restype = C.c_int
+        self.lib.refh_get_boxes_b200.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_int]
+        n = self.lib.refh_get_boxes_b200(self.h, w, h, thresh, nms, out.ctypes.data_as(C.c_void_p), max_out)
+        return out[:min(n, max_out)]
+
     def get_boxes(self, w: int, h: int, thresh: float, nms: float, max_out: int = 200000):
         classes = self.layers[-1]["classes"]
         out = np.zeros((max_out, 6 + classes), np.float32)

@@ -278,4 +278,22 @@ float *refh_predict_b200(refh *h, float *input)
 {
     return h->quantized ? network_predict_b200_quantized(h->net, input) : network_predict_b200(h->net, input);
 }
+/* the glue's device-side decode + NMS, reported in refh_get_boxes' row format */
+detection *get_network_boxes_nms_b200(network *net, int w, int h, float thresh, float nms, int relative, int *num, int letter);
+int refh_get_boxes_b200(refh *h, int w, int hgt, float thresh, float nms, float *out, int max_out)
+{
+    int nboxes = 0, k, c;
+    detection *dets = get_network_boxes_nms_b200(&h->net, w, hgt, thresh, nms, 1, &nboxes, 0);
+    layer l = h->net.layers[h->net.n - 1];
+    int stride = 6 + l.classes;
+    int n = nboxes < max_out ? nboxes : max_out;
+    for (k = 0; k < n; ++k) {
+        float *o = out + (size_t)k * stride;
+        o[0] = dets[k].bbox.x; o[1] = dets[k].bbox.y; o[2] = dets[k].bbox.w; o[3] = dets[k].bbox.h;
+        o[4] = dets[k].objectness; o[5] = 0;
+        for (c = 0; c < l.classes; ++c) o[6 + c] = dets[k].prob[c];
+    }
+    free_detections(dets, nboxes);
+    return nboxes;
+}
 #endif

@@ -290,6 +290,15 @@ def test_true_dropin_behind_reference_host_code(name, q, workdir):
         assert util.rel_l2(net.output(i), cpu_out[i]) <= tol, (name, q, i)
     gpu_boxes = net.get_boxes(640, 480, 0.25, 0.45)
     assert abs(gpu_boxes.shape[0] - cpu_boxes.shape[0]) <= max(2, cpu_boxes.shape[0] // 50)
+    # the glue's device-side decode + NMS (get_network_boxes_nms_b200) == the reference's decoder run on the very
+    # tensors network_predict_b200 put into l.output
+    dev = net.get_boxes_b200(640, 480, 0.25, 0.45)
+    assert dev.shape[0] == gpu_boxes.shape[0]
+    if dev.shape[0]:
+        a = np.delete(dev, 5, axis=1); e = np.delete(gpu_boxes, 5, axis=1)
+        a = a[np.lexsort(a[:, :4].T[::-1])]; e = e[np.lexsort(e[:, :4].T[::-1])]
+        assert np.allclose(a[:, :4], e[:, :4], rtol=1e-6, atol=1e-7)
+        assert np.array_equal(a[:, 4:], e[:, 4:])
 
 
 @pytest.mark.parametrize("src_hw", [(48, 80), (64, 64), (97, 131), (200, 33)])
