@@ -10,7 +10,7 @@
 //        mode 1: the same tiles as all others (weights: unicast, shared -- does L2 de-duplicate?)
 //        mode 2: 1/CS of each shared tile, multicast to the CS CTAs of its cluster.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tma_mcast_probe tma_mcast_probe.cu
-// NOT RUN YET (written when the round's GPU budget was spent): expect to fix details on first contact.
+// Result of the first run: profiles/r01_tma_mcast_probe.txt (64 B/clk/SM unicast, 62 with multicast, 33 clusters of 4).
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
