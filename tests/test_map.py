@@ -91,3 +91,33 @@ def test_map_accounting_equals_reference(name, iou_thresh, workdir):
     for mine, theirs in zip((st["precision"], st["recall"], st["f1"]), prf):
         assert abs(mine - float(theirs)) <= 0.00501 or (np.isnan(mine) and "nan" in theirs)
     assert int(tp) > 0 and mAP > 0                                       # the dataset exercises the matching at all
+
+
+def test_dataset_reader_matches_what_the_reference_reads(workdir):
+    """BMP / PPM decode, the label-path rewriting and the label parser of yolo2_light_b200.dataset on the files the
+    mAP parity test writes: the reference's loader must see the same pixels (its resize of them == ours of them)."""
+    from yolo2_light_b200 import dataset
+    from oracle import ref
+    root = os.path.join(workdir, "reader")
+    os.makedirs(os.path.join(root, "images"), exist_ok=True)
+    os.makedirs(os.path.join(root, "labels"), exist_ok=True)
+    rng = np.random.default_rng(3)
+    for w, h in ((80, 72), (33, 50)):                       # a width whose rows need BMP padding, too
+        img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        p = os.path.join(root, "images", f"i{w}.bmp")
+        _write_bmp(p, img)
+        assert np.array_equal(dataset.read_image_u8(p), img)
+        ppm = os.path.join(root, "images", f"i{w}.ppm")
+        open(ppm, "wb").write(b"P6\n# c\n%d %d\n255\n" % (w, h) + img.tobytes())
+        assert np.array_equal(dataset.read_image_u8(ppm), img)
+        assert dataset.label_path(p) == os.path.join(root, "labels", f"i{w}.txt")
+    lab = os.path.join(root, "labels", "i80.txt")
+    open(lab, "w").write("3 0.5 0.25 0.125 0.0625\n7 0.1 0.2 0.3 0.4\n")
+    got = dataset.read_labels(lab)
+    assert got.shape == (2, 5) and got[1, 0] == 7 and np.allclose(got[0], [3, 0.5, 0.25, 0.125, 0.0625])
+    assert dataset.read_labels(os.path.join(root, "labels", "missing.txt")).shape == (0, 5)
+    open(os.path.join(root, "valid.txt"), "w").write(os.path.join(root, "images", "i80.bmp") + "\n")
+    open(os.path.join(root, "names.txt"), "w").write("a\nb\n")
+    open(os.path.join(root, "d.cfg"), "w").write(f"classes= 2\nvalid  = {root}/valid.txt\nnames = {root}/names.txt\n# x\n")
+    paths, names, truth = dataset.load_validation_set(os.path.join(root, "d.cfg"))
+    assert len(paths) == 1 and names == ["a", "b"] and truth.shape == (2, 6) and truth[1, 1] == 7
