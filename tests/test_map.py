@@ -121,3 +121,41 @@ def test_dataset_reader_matches_what_the_reference_reads(workdir):
     open(os.path.join(root, "d.cfg"), "w").write(f"classes= 2\nvalid  = {root}/valid.txt\nnames = {root}/names.txt\n# x\n")
     paths, names, truth = dataset.load_validation_set(os.path.join(root, "d.cfg"))
     assert len(paths) == 1 and names == ["a", "b"] and truth.shape == (2, 6) and truth[1, 1] == 7
+
+
+def test_map_driver_loop_equals_reference_end_to_end(workdir):
+    """dataset.evaluate_map (the loop of tools/map.py) with the forward + decoder supplied by the reference through a
+    stand-in object: same files in, same mAP out as validate_detector_map.  (The GPU stand-ins of the two calls are
+    parity-tested on their own: test_gpu_detect.py, test_device_input_pipeline_bit_exact.)"""
+    import yolo2_light_b200 as yb
+    from yolo2_light_b200 import dataset
+    from oracle import ref
+    name = "tiny64"
+    cfg, wts = util.model_files(name, workdir)
+    rnet = ref.RefNet(cfg, wts, 1, 0, 7)
+    classes = rnet.layers[-1]["classes"]
+    root = os.path.join(workdir, "mapset_tiny64_50")          # written by test_map_accounting_equals_reference
+    if not os.path.exists(os.path.join(root, "data.cfg")):
+        test_map_accounting_equals_reference(name, 0.5, workdir)
+    paths, names, truth = dataset.load_validation_set(os.path.join(root, "data.cfg"))
+    assert len(paths) == 7 and len(names) == classes and truth.shape[0] > 0
+
+    class RefBacked:
+        batch = 2                                               # exercises the padded last batch (7 images)
+
+        def predict_image_u8(self, imgs, quantized=False):
+            self.imgs = imgs
+
+        def detect(self, w, h, thresh, nms, relative=1, letter=0, max_rows=1024, quantized=False):
+            dets = []
+            for im in self.imgs:
+                rnet.predict(ref.load_resize_u8(im, rnet.width, rnet.height)[None])
+                dets.append(np.delete(rnet.get_boxes(w, h, thresh, nms), 5, axis=1))
+            return dets, np.array([d.shape[0] for d in dets], np.int32)
+
+    mAP, aps, st = dataset.evaluate_map(RefBacked(), paths, truth, classes, 0.5, 0.24)
+    out = open(os.path.join(root, "ref_stdout.txt")).read()
+    map_ref = float(re.search(r"mean average precision \(mAP\) = ([0-9.]+)", out).group(1))
+    tp, fp, fn = re.search(r"TP = (\d+), FP = (\d+), FN = (\d+)", out).groups()
+    assert abs(mAP - map_ref) < 5e-7
+    assert (int(st["tp"]), int(st["fp"]), int(st["fn"])) == (int(tp), int(fp), int(fn))

@@ -92,3 +92,40 @@ def load_validation_set(datacfg: str):
         for row in read_labels(label_path(p)):
             truth.append((float(k), *row))
     return paths, names, np.array(truth, np.float32).reshape(-1, 6)
+
+
+def evaluate_map(net, paths, truth: np.ndarray, classes: int, iou_thresh: float = 0.5, thresh_calc_avg_iou: float = 0.24,
+                 max_rows: int = 8192, quantized: bool = False, progress=None):
+    """The loop of ``validate_detector_map`` (additionally.c:4614-4780) around any object with ``batch``,
+    ``predict_image_u8(images_u8[batch, h, w, 3], quantized=)`` and ``detect(w, h, thresh, nms, relative=, letter=,
+    max_rows=, quantized=)`` -- ``yolo2_light_b200.Network`` -- then ``yb_map_evaluate``.  Returns (mAP, ap[classes], stats)."""
+    from . import api
+    rows = []
+    B = net.batch
+    done = 0
+
+    def flush(chunk):
+        nonlocal done
+        n = len(chunk)
+        while len(chunk) < B:
+            chunk.append(chunk[-1])                                # pad the batch; its extra rows are dropped
+        net.predict_image_u8(np.stack(chunk), quantized=quantized)
+        # the reference's settings: thresh .005, nms .45, relative coordinates (get_network_boxes(net, 1, 1, ...), :4657)
+        dets, counts = net.detect(1, 1, 0.005, 0.45, relative=0, letter=0, max_rows=max_rows, quantized=quantized)
+        if max(counts[:n]) > max_rows:
+            raise ValueError(f"{max(counts[:n])} candidates in one image, only {max_rows} kept: raise max_rows")
+        rows.extend(dets[:n])
+        done += n
+        if progress:
+            progress(done, len(paths))
+
+    chunk = []
+    for p in paths:                                                # images of one size share a batch, order is kept
+        img = read_image_u8(p)
+        if chunk and (img.shape != chunk[0].shape or len(chunk) == B):
+            flush(chunk)
+            chunk = []
+        chunk.append(img)
+    if chunk:
+        flush(chunk)
+    return api.map_evaluate(rows, truth, classes, iou_thresh, thresh_calc_avg_iou)
