@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 
 #include "yb_engine.h"
@@ -81,7 +82,9 @@ void yb_quantinization_and_get_multipliers(yb_network *net) {
 yb_network *yb_network_from_layers(const yb_layer_desc *layers, int n_layers, int batch, int h, int w, int c,
                                    int quantized) {
     YB_TRY
-    yb_network *hnd = new yb_network();
+    if (!layers || n_layers <= 0 || batch <= 0 || h <= 0 || w <= 0 || c <= 0) fatal_throw("from_layers: bad arguments");
+    std::unique_ptr<yb_network> hold(new yb_network());   // released to the caller only when every layer validated
+    yb_network *hnd = hold.get();
     Network &net = hnd->net;
     net.batch = batch; net.h = h; net.w = w; net.c = c; net.inputs = h * w * c; net.quantized = quantized;
     net.layers.resize(n_layers);
@@ -118,7 +121,7 @@ yb_network *yb_network_from_layers(const yb_layer_desc *layers, int n_layers, in
             break;
         }
         case YB_ROUTE:
-            if (!d.input_layers) fatal_throw("from_layers: route without input_layers");
+            if (!d.input_layers || l.n <= 0) fatal_throw("from_layers: route without input_layers");
             l.input_layers.assign(d.input_layers, d.input_layers + l.n);
             l.outputs = 0;
             for (int s : l.input_layers) {
@@ -128,20 +131,30 @@ yb_network *yb_network_from_layers(const yb_layer_desc *layers, int n_layers, in
             }
             break;
         case YB_YOLO:
-            if (d.mask) l.mask.assign(d.mask, d.mask + l.n);
-            if (d.anchors) l.anchors.assign(d.anchors, d.anchors + 2 * (size_t)l.total);
+            // the decoders index anchors[2 * mask[a]] for a < n: reject descriptions that would read out of bounds
+            if (!d.mask || !d.anchors || l.n <= 0 || l.total <= 0) fatal_throw("from_layers: yolo layer without mask / anchors");
+            l.mask.assign(d.mask, d.mask + l.n);
+            for (int m : l.mask) if (m < 0 || m >= l.total) fatal_throw("from_layers: yolo mask entry out of range");
+            l.anchors.assign(d.anchors, d.anchors + 2 * (size_t)l.total);
+            if (i == 0 || l.c != l.n * (l.classes + 4 + 1) || net.layers[i - 1].out_c != l.c)
+                fatal_throw("from_layers: yolo layer " + std::to_string(i) + " does not match its input's channel count");
             l.outputs = l.h * l.w * l.n * (l.classes + 4 + 1);
             break;
         case YB_REGION:
-            if (d.anchors) l.anchors.assign(d.anchors, d.anchors + 2 * (size_t)l.n);
+            if (!d.anchors || l.n <= 0) fatal_throw("from_layers: region layer without anchors");
+            l.anchors.assign(d.anchors, d.anchors + 2 * (size_t)l.n);
             l.outputs = l.h * l.w * l.n * (l.classes + l.coords + 1);
+            break;
+        case YB_SHORTCUT:
+            if (l.index < 0 || l.index >= i) fatal_throw("from_layers: bad shortcut index");
+            l.outputs = l.out_h * l.out_w * l.out_c;
             break;
         default:
             l.outputs = l.out_h * l.out_w * l.out_c;
             break;
         }
     }
-    return hnd;
+    return hold.release();
     YB_CATCH(nullptr)
 }
 
@@ -195,13 +208,13 @@ void yb_set_batch_network(yb_network *net, int batch) { set_batch(&net->net, bat
 
 int yb_network_set_device(yb_network *n, int device) {
     n->net.device = device;
-    n->net.engine[0].reset(); n->net.engine[1].reset();
+    drop_engines(&n->net);
     return 0;
 }
 int yb_network_set_precision(yb_network *n, int precision) {
     if (precision != YB_PREC_BF16_TC && precision != YB_PREC_FP32) { report("bad precision"); return -1; }
     n->net.precision = precision;
-    n->net.engine[0].reset(); n->net.engine[1].reset();
+    drop_engines(&n->net);
     return 0;
 }
 /* diagnostic switches (tests): fusion on/off, keep raw integer results, INT8 rule index offset */
@@ -212,7 +225,7 @@ int yb_network_set_option(yb_network *n, const char *name, int value) {
     else if (!strcmp(name, "q_index_offset")) net.q_index_offset = value;
     else if (!strcmp(name, "ksplit")) net.ksplit = value != 0;
     else { report(std::string("unknown option ") + name); return -1; }
-    net.engine[0].reset(); net.engine[1].reset();
+    drop_engines(&net);
     return 0;
 }
 
@@ -370,8 +383,11 @@ int yb_network_detect(yb_network *n, int quantized, int w, int h, float thresh, 
 int yb_network_calibrate(yb_network *n, const float *input, float *multipliers, int max_values) {
     YB_TRY
     Network &net = n->net;
-    const bool old_fuse = net.fuse;
-    if (old_fuse) { net.fuse = false; net.engine[0].reset(); }          // every layer input must exist in memory
+    struct FuseGuard {   // every layer input must exist in memory: fusion off for the calibration engine, restored on any exit
+        Network &net; bool old;
+        explicit FuseGuard(Network &n_) : net(n_), old(n_.fuse) { if (old) { net.fuse = false; drop_engines(&net); } }
+        ~FuseGuard() { if (old) { net.fuse = true; drop_engines(&net); } }
+    } guard(net);
     Engine *e = get_engine(n, 0);
     engine_upload_input(e, input, nullptr);
     engine_forward(e, nullptr, nullptr);
@@ -388,7 +404,6 @@ int yb_network_calibrate(yb_network *n, const float *input, float *multipliers, 
             multipliers[(size_t)b * nconv + k++] = entropy_from_histogram(hist.data(), 1.0f / 16, 4096);
         }
     }
-    if (old_fuse) { net.fuse = true; net.engine[0].reset(); }
     return nconv;
     YB_CATCH(-1)
 }

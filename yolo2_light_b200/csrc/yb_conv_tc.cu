@@ -291,7 +291,9 @@ __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
 // TMA unit per FLOP drop by a third; that unit (~64 B/clk/SM) is what bounds the BN=256 layers
 // (profiles/r01_notes.md).  The leader CTA (cluster rank 0) issues the MMAs for both.
 // KS: compiled with the K-split tail schedule (TcParams::sk_T); the KS = false instantiations carry none of its code.
-template <int CG, bool KS>
+// ST: compiled with the per-role cycle counters of YB_TC_STATS=1 (diagnostic); the production instantiations (ST = false)
+// contain no clock64() reads -- the single-thread producer / MMA roles are issue-bound on the BN <= 128 layers.
+template <int CG, bool KS, bool ST>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -360,7 +362,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // ======================= TMA producer (every CTA loads its own A rows and its share of B) ===========
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
-            long long w_empty = 0, w_tma = 0; const long long t_begin = clock64();
+            long long w_empty = 0, w_tma = 0; const long long t_begin = ST ? clock64() : 0;
             // loop-invariant parameters in registers; the (tap, channel-block) walk is incremental -- the first version
             // recomputed it with two integer divisions per K-block, and that ~700-cycle dependent scalar chain in
             // this single thread was what starved the tensor pipe (profiles/r01_notes.md)
@@ -387,7 +389,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 int cb = kb_begin - tap0 * cblocks, ky = tap0 / fsize, kx = tap0 - (tap0 / fsize) * fsize, kcol = kb_begin * BK;
                 for (int kb0 = kb_begin; kb0 < kb_end; kb0 += sps) {
                     const int nsub = min(sps, kb_end - kb0);
-                    { const long long c0 = clock64(); mbar_wait(empty_bar(stage), phase ^ 1u, 0); w_empty += clock64() - c0; }
+                    if constexpr (ST) { const long long c0 = clock64(); mbar_wait(empty_bar(stage), phase ^ 1u, 0); w_empty += clock64() - c0; }
+                    else mbar_wait(empty_bar(stage), phase ^ 1u, 0);
                     const uint32_t fb = full_bar(stage);
                     const uint32_t a_dst = smem0 + (uint32_t)stage * stage_bytes;
                     const uint32_t b_dst = a_dst + b_off;
@@ -398,7 +401,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     }
                     // the leader's barrier collects the bytes of BOTH CTAs (the 2-CTA TMA form signals the leader)
                     if (leader) mbar_arrive_expect_tx(fb, (uint32_t)(CG * nsub) * (a_bytes + (bstat ? 0u : b_bytes)));
-                    const long long ct0 = clock64();
+                    const long long ct0 = ST ? clock64() : 0;
                     for (int j = 0; j < nsub; ++j) {
                         const uint32_t ad = a_dst + (uint32_t)j * a_bytes, bd = b_dst + (uint32_t)j * b_bytes;
                         const int c0 = cb * BK;
@@ -414,11 +417,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         kcol += BK;
                         if (++cb == cblocks) { cb = 0; if (++kx == fsize) { kx = 0; ++ky; } }
                     }
-                    w_tma += clock64() - ct0;
+                    if constexpr (ST) w_tma += clock64() - ct0;
                     if (++stage == stages) { stage = 0; phase ^= 1u; }
                 }
             }
-            if (p.stats) { p.stats[blockIdx.x * 8 + 0] = (unsigned long long)w_empty; p.stats[blockIdx.x * 8 + 1] = (unsigned long long)(clock64() - t_begin); p.stats[blockIdx.x * 8 + 7] = (unsigned long long)w_tma; }
+            if (ST && p.stats) { p.stats[blockIdx.x * 8 + 0] = (unsigned long long)w_empty; p.stats[blockIdx.x * 8 + 1] = (unsigned long long)(clock64() - t_begin); p.stats[blockIdx.x * 8 + 7] = (unsigned long long)w_tma; }
         }
     } else if (warp == 1) {
         // ======================= MMA issuer (CG=2: the leader CTA only, for both CTAs) =======================
@@ -432,19 +435,23 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const uint32_t a_bytes = p.a_bytes, b_bytes = p.b_bytes, stage_bytes = p.stage_bytes, idesc = p.idesc, dbg = (uint32_t)p.dbg;
             const uint32_t b_off = (uint32_t)sps * a_bytes;
             const uint64_t hi = (uint64_t)p.desc_hi << 32;
-            long long w_full = 0, w_tempty = 0; const long long t_begin = clock64();
+            long long w_full = 0, w_tempty = 0; const long long t_begin = ST ? clock64() : 0;
             const int bstat = p.bstat;
             if (bstat) { mbar_wait(bstat_bar, 0, 4); tc_fence_after(); }
             TcSched sch = sched_init<KS>(p, w_first, w_step);
             int w, seg0, seg1;
             while (sched_next<KS>(sch, w, seg0, seg1)) {
-                { const long long c0 = clock64(); mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 1); w_tempty += clock64() - c0; }   // epilogue(s) drained this accumulator
+                // epilogue(s) drained this accumulator
+                if constexpr (ST) { const long long c0 = clock64(); mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 1); w_tempty += clock64() - c0; }
+                else mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                 const int kb_begin = seg0 * sps, kb_end = min(kblocks, seg1 * sps);
                 for (int kb0 = kb_begin; kb0 < kb_end; kb0 += sps) {
                     const int nsub = min(sps, kb_end - kb0);
-                    { const long long c0 = clock64(); mbar_wait(full_bar(stage), phase, 2); w_full += clock64() - c0; }   // TMA bytes have landed
+                    // TMA bytes have landed
+                    if constexpr (ST) { const long long c0 = clock64(); mbar_wait(full_bar(stage), phase, 2); w_full += clock64() - c0; }
+                    else mbar_wait(full_bar(stage), phase, 2);
                     tc_fence_after();
                     const uint32_t a_base = smem0 + (uint32_t)stage * stage_bytes;
                     const uint32_t b_base = a_base + b_off;
@@ -471,7 +478,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 if constexpr (CG == 2) umma2_commit_both(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
                 if (++acc == TC_ACC) { acc = 0; acc_phase ^= 1u; }
             }
-            if (p.stats) { p.stats[blockIdx.x * 8 + 2] = (unsigned long long)w_full; p.stats[blockIdx.x * 8 + 3] = (unsigned long long)w_tempty;
+            if (ST && p.stats) { p.stats[blockIdx.x * 8 + 2] = (unsigned long long)w_full; p.stats[blockIdx.x * 8 + 3] = (unsigned long long)w_tempty;
                            p.stats[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_begin); }
         };
         if (leader && elect_one()) {
@@ -493,7 +500,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int tx = r & (p.TW - 1), ty = r >> p.TWlog2;
         const bool leaky = p.act == ACT_LEAKY, leaky2 = p.act2 == ACT_LEAKY;
         int acc = 0; uint32_t acc_phase = 0;
-        long long w_tfull = 0; const long long t_begin = clock64();
+        long long w_tfull = 0; const long long t_begin = ST ? clock64() : 0;
         TcSched sch = sched_init<KS>(p, w_first, w_step);
         int w, seg0, seg1;
         while (sched_next<KS>(sch, w, seg0, seg1)) {
@@ -524,13 +531,16 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         dst[g] = __ldg(reinterpret_cast<const uint4 *>(rrow + (size_t)(n0 + f0) * 2) + g);
                 }
             };
-            const bool coalesced = (p.out_bf16 && ((cend - cbeg) >= 64 || (cend - cbeg) == 32) && !p.no_coalesce) || p.kind != 0;
-            if (!coalesced) {
+            // the staged bf16 store paths fetch their own residual, the integer / tf32 kinds never have one: rv[] is only
+            // prefetched for the per-thread store path (f32 heads, YB_TC_NO_COALESCE)
+            const bool own_res = (p.out_bf16 && ((cend - cbeg) >= 64 || (cend - cbeg) == 32) && !p.no_coalesce) || p.kind != 0 || !p.res;
+            if (!own_res) {
                 if (cbeg < cend) load_res(cbeg, rv[0]);
                 if (cend - cbeg > 32) load_res(cbeg + 32, rv[1]);
             }
 
-            { const long long c0 = clock64(); mbar_wait(tfull_bar(acc), acc_phase, 3); w_tfull += clock64() - c0; }
+            if constexpr (ST) { const long long c0 = clock64(); mbar_wait(tfull_bar(acc), acc_phase, 3); w_tfull += clock64() - c0; }
+            else mbar_wait(tfull_bar(acc), acc_phase, 3);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
 
@@ -907,7 +917,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             if (lane == 0) { if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_remote(tempty_bar(acc), 0); }
             if (++acc == TC_ACC) { acc = 0; acc_phase ^= 1u; }
         }
-        if (p.stats && warp == 2 && lane == 0) { p.stats[blockIdx.x * 8 + 5] = (unsigned long long)w_tfull; p.stats[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - t_begin); }
+        if (ST && p.stats && warp == 2 && lane == 0) { p.stats[blockIdx.x * 8 + 5] = (unsigned long long)w_tfull; p.stats[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - t_begin); }
     }
 
     tc_fence_before();
@@ -1229,10 +1239,12 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
     }
     plan->smem = (size_t)p.stages * p.stage_bytes + p.bstat_bytes + 1024 /*alignment slack*/ + 8 * (2 * p.stages + 2 * TC_ACC + 1) + 16 +
                  sizeof(float) * (size_t)p.nt * BN /*bias*/ + (size_t)p.nt * BN / 8 /*yolo mask*/ + 128 + 4096 * TC_EPI_WARPS /*epilogue staging*/;
-    if (cudaFuncSetAttribute(k_conv_tc<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(k_conv_tc<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(k_conv_tc<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(k_conv_tc<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(k_conv_tc<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_conv_tc<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_conv_tc<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_conv_tc<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_conv_tc<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_conv_tc<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
         fatal_throw("cudaFuncSetAttribute(k_conv_tc) failed");
     return plan;
 }
@@ -1387,12 +1399,15 @@ void tc_launch(void *vp, cudaStream_t s) {
     cfg.attrs = attr; cfg.numAttrs = na;
     static const bool ks_always = getenv("YB_TC_KS_ALWAYS") != nullptr;   // experiment: one kernel variant for every layer
     const bool ks = plan->p.sk_T > 0 || ks_always;
+    const bool st = plan->p.stats != nullptr && !ks;   // role counters: a separate instantiation (YB_TC_STATS=1)
     if (plan->p.cg == 2) {
-        if (ks) cudaLaunchKernelEx(&cfg, k_conv_tc<2, true>, plan->tmA, plan->tmB, plan->p);
-        else cudaLaunchKernelEx(&cfg, k_conv_tc<2, false>, plan->tmA, plan->tmB, plan->p);
+        if (ks) cudaLaunchKernelEx(&cfg, k_conv_tc<2, true, false>, plan->tmA, plan->tmB, plan->p);
+        else if (st) cudaLaunchKernelEx(&cfg, k_conv_tc<2, false, true>, plan->tmA, plan->tmB, plan->p);
+        else cudaLaunchKernelEx(&cfg, k_conv_tc<2, false, false>, plan->tmA, plan->tmB, plan->p);
     } else {
-        if (ks) cudaLaunchKernelEx(&cfg, k_conv_tc<1, true>, plan->tmA, plan->tmB, plan->p);
-        else cudaLaunchKernelEx(&cfg, k_conv_tc<1, false>, plan->tmA, plan->tmB, plan->p);
+        if (ks) cudaLaunchKernelEx(&cfg, k_conv_tc<1, true, false>, plan->tmA, plan->tmB, plan->p);
+        else if (st) cudaLaunchKernelEx(&cfg, k_conv_tc<1, false, true>, plan->tmA, plan->tmB, plan->p);
+        else cudaLaunchKernelEx(&cfg, k_conv_tc<1, false, false>, plan->tmA, plan->tmB, plan->p);
     }
 }
 

@@ -108,9 +108,11 @@ static __global__ void __launch_bounds__(256) k_det_emit(DetParams P, const int 
     } else {
         const int index = cell * l.n + a;
         const float *q = p + (size_t)index * (l.classes + 5);
-        // get_region_box_cpu, yolov2_forward_network.c:653-661: x, y through a double-precision logistic
-        x = (float)(((double)col + 1. / (1. + exp(-(double)q[0]))) / (double)l.w);
-        y = (float)(((double)row + 1. / (1. + exp(-(double)q[1]))) / (double)l.h);
+        // get_region_box_cpu, yolov2_forward_network.c:653-661: logistic_activate evaluates in double but RETURNS float
+        // (additionally.h:85); the add and the divide are then float operations
+        const float lx = (float)(1. / (1. + exp(-(double)q[0]))), ly = (float)(1. / (1. + exp(-(double)q[1])));
+        x = __fdiv_rn(__fadd_rn((float)col, lx), (float)l.w);
+        y = __fdiv_rn(__fadd_rn((float)row, ly), (float)l.h);
         w = __fdiv_rn(__fmul_rn(expf(q[2]), l.aw[a]), (float)l.w);
         h = __fdiv_rn(__fmul_rn(expf(q[3]), l.ah[a]), (float)l.h);
         obj = 1.f;

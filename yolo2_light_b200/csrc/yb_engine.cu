@@ -430,14 +430,16 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                             dst[(size_t)f * K + (size_t)t * l.c + c] =
                                 __float2bfloat16_rn(l.weights[((size_t)f * l.c + c) * taps + t]);
             } else {
-                // f32 [K][ldw], K ordered (ky, kx, c)
+                // f32 [K][ldw]; K ordered (ky, kx, c), or -- f32 activations: the exact order of the reference's gemm_nn
+                // (k_conv_simt<EXACT>) -- (c, ky, kx)
                 w.ldw = (int)align_up(l.n, 64);
                 w.w_f32 = reserve(sizeof(float) * (size_t)K * w.ldw);
                 float *dst = reinterpret_cast<float *>(&hostw[w.w_f32]);
                 for (int f = 0; f < l.n; ++f)
                     for (int c = 0; c < l.c; ++c)
                         for (int t = 0; t < taps; ++t)
-                            dst[((size_t)t * l.c + c) * w.ldw + f] = l.weights[((size_t)f * l.c + c) * taps + t];
+                            dst[(ADT == DT_F32 ? (size_t)c * taps + t : (size_t)t * l.c + c) * w.ldw + f] =
+                                l.weights[((size_t)f * l.c + c) * taps + t];
             }
         } else if (v == 1 && xnor_on_tc(l)) {
             // +-1 bytes [ldn][taps][C]: +1 where w > 0, -1 otherwise; padded filter rows stay 0
@@ -538,9 +540,9 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
             e->first_kind = OP_CONV_SIMT; e->first_layer = 0;
             e->first_op = [=](const float *din, cudaStream_t s) {
                 if (nf == 32 && odt == DT_BF16) k_conv_stem<32, __nv_bfloat16><<<grid, 128, 0, s>>>(din, tout, w32, act, H, W);
-                else if (nf == 32) k_conv_stem<32, float><<<grid, 128, 0, s>>>(din, tout, w32, act, H, W);
+                else if (nf == 32) k_conv_stem<32, float, true><<<grid, 128, 0, s>>>(din, tout, w32, act, H, W);
                 else if (odt == DT_BF16) k_conv_stem<16, __nv_bfloat16><<<grid, 128, 0, s>>>(din, tout, w16, act, H, W);
-                else k_conv_stem<16, float><<<grid, 128, 0, s>>>(din, tout, w16, act, H, W);
+                else k_conv_stem<16, float, true><<<grid, 128, 0, s>>>(din, tout, w16, act, H, W);
             };
         } else {
             const TV in0 = e->in0;
@@ -628,7 +630,7 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                     const int key = in_dt * 4 + odt * 2 + rdt;
                     e->ops.push_back(Op{OP_CONV_SIMT, i, [p, grid, key](cudaStream_t s) {
                         switch (key) {
-                        case 0: k_conv_simt<float, float, float><<<grid, 256, 0, s>>>(p); break;
+                        case 0: k_conv_simt<float, float, float, true><<<grid, 256, 0, s>>>(p); break;   // reference order, bit-exact
                         case 1: k_conv_simt<float, float, __nv_bfloat16><<<grid, 256, 0, s>>>(p); break;
                         case 2: k_conv_simt<float, __nv_bfloat16, float><<<grid, 256, 0, s>>>(p); break;
                         case 3: k_conv_simt<float, __nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, s>>>(p); break;

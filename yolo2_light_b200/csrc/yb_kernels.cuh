@@ -140,7 +140,11 @@ struct ConvP {
     long M;                    // N*out_h*out_w
 };
 
-template <typename TIn, typename TOut, typename TRes>
+// EXACT = true (f32 activations: the exact nets and YB_PREC_FP32): K runs in the reference's own order (c, ky, kx) --
+// weights [K][ldw] stored in that order -- and every product and sum is rounded separately (__fmul_rn / __fadd_rn), i.e.
+// gemm_nn's `C[j] += A_PART * B[k][j]` of the scalar build (additionally.c:1272-1286): the result is bit-identical to the
+// reference, so a last-bit difference can never flip `x > 0` / `(int16)(x * m)` in a following integer layer.
+template <typename TIn, typename TOut, typename TRes, bool EXACT = false>
 __global__ void __launch_bounds__(256) k_conv_simt(ConvP p) {
     constexpr int BM = 64, BN = 64, BK = 16;
     __shared__ float As[BK][BM + 4];
@@ -179,7 +183,8 @@ __global__ void __launch_bounds__(256) k_conv_simt(ConvP p) {
             const int k = k0 + lk + q;
             float v = 0.f;
             if (lvalid && k < p.K) {
-                const int tap = k / C, ch = k - tap * C;
+                const int taps = p.size * p.size;
+                const int tap = EXACT ? k % taps : k / C, ch = EXACT ? k / taps : k - tap * C;
                 const int ky = tap / p.size, kx = tap - ky * p.size;
                 const int iy = liy0 + ky, ix = lix0 + kx;
                 if (iy >= 0 && iy < p.in.H && ix >= 0 && ix < p.in.W) v = to_f32(tv_px<TIn>(p.in, ln, iy, ix)[ch]);
@@ -203,7 +208,10 @@ __global__ void __launch_bounds__(256) k_conv_simt(ConvP p) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) {
+                    if constexpr (EXACT) acc[i][j] = __fadd_rn(acc[i][j], __fmul_rn(b[j], a[i]));
+                    else acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                }
         }
         __syncthreads();
     }
@@ -220,8 +228,8 @@ __global__ void __launch_bounds__(256) k_conv_simt(ConvP p) {
         for (int j = 0; j < 4; ++j) {
             const int f = n0 + tx * 4 + j;
             if (f >= p.n) continue;
-            float v = act_exact(acc[i][j] + p.bias[f], p.act);
-            if (r) v = act_exact(v + to_f32(r[f]), p.act2);
+            float v = act_exact(__fadd_rn(acc[i][j], p.bias[f]), p.act);
+            if (r) v = act_exact(__fadd_rn(v, to_f32(r[f])), p.act2);
             o[f] = from_f32<TOut>(v);
         }
     }
@@ -240,7 +248,9 @@ struct StemW {            // passed by value as a kernel parameter: lives in the
     float b[NF];
 };
 
-template <int NF, typename TOut>
+// EXACT (f32 output = the exact nets): reference order (c, ky, kx) with separately rounded products and sums, see
+// k_conv_simt -- the INT8 / XNOR layers behind the stem then see bit-identical inputs.
+template <int NF, typename TOut, bool EXACT = false>
 __global__ void __launch_bounds__(128) k_conv_stem(const float *__restrict__ in, TV out, const __grid_constant__ StemW<NF> sw,
                                                    int act, int H, int W) {
     const long total = (long)out.N * H * W;
@@ -253,6 +263,23 @@ __global__ void __launch_bounds__(128) k_conv_stem(const float *__restrict__ in,
     float acc[NF];
 #pragma unroll
     for (int f = 0; f < NF; ++f) acc[f] = 0.f;
+    if constexpr (EXACT) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int iy = y + ky - 1;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int ix = x + kx - 1;
+                    const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+                    const float v = ok ? __ldg(img + ((size_t)c * H + iy) * W + ix) : 0.f;
+#pragma unroll
+                    for (int f = 0; f < NF; ++f)
+                        acc[f] = __fadd_rn(acc[f], __fmul_rn(sw.w[((ky * 3 + kx) * 3 + c) * NF + f], v));
+                }
+            }
+    } else {
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
         const int iy = y + ky - 1;
@@ -267,6 +294,7 @@ __global__ void __launch_bounds__(128) k_conv_stem(const float *__restrict__ in,
                 for (int f = 0; f < NF; ++f) acc[f] = fmaf(v, sw.w[((ky * 3 + kx) * 3 + c) * NF + f], acc[f]);
             }
         }
+    }
     }
     TOut *o = tv_px<TOut>(out, n, y, x);
     if constexpr (sizeof(TOut) == 2) {
@@ -290,8 +318,8 @@ __global__ void __launch_bounds__(128) k_conv_stem(const float *__restrict__ in,
         float4 *op = reinterpret_cast<float4 *>(o);   // NF*4 bytes per pixel, 16-byte aligned (ldc % 4 == 0)
 #pragma unroll
         for (int g = 0; g < NF / 4; ++g)
-            op[g] = make_float4(act_exact(acc[g * 4 + 0] + sw.b[g * 4 + 0], act), act_exact(acc[g * 4 + 1] + sw.b[g * 4 + 1], act),
-                                act_exact(acc[g * 4 + 2] + sw.b[g * 4 + 2], act), act_exact(acc[g * 4 + 3] + sw.b[g * 4 + 3], act));
+            op[g] = make_float4(act_exact(__fadd_rn(acc[g * 4 + 0], sw.b[g * 4 + 0]), act), act_exact(__fadd_rn(acc[g * 4 + 1], sw.b[g * 4 + 1]), act),
+                                act_exact(__fadd_rn(acc[g * 4 + 2], sw.b[g * 4 + 2]), act), act_exact(__fadd_rn(acc[g * 4 + 3], sw.b[g * 4 + 3]), act));
     }
 }
 

@@ -17,6 +17,14 @@ namespace yb {
 
 void fatal_throw(const std::string &msg) { throw Error{msg}; }
 
+// Every host `Layer::output` points into pinned memory owned by an Engine: whenever the engines go, those pointers go
+// with them (a stale non-null pointer would make get_boxes / yb_network_layer_output read freed memory).
+void drop_engines(Network *net) {
+    net->engine[0].reset();
+    net->engine[1].reset();
+    for (Layer &l : net->layers) { l.output = nullptr; l.output_count = 0; }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // .cfg reader.  Grammar of read_cfg / read_option (additionally.c:3423-3457, :3282-3300): every blank
 // (space, tab, CR, LF) is removed from a line first; '[' starts a section; '#', ';' and empty lines are
@@ -258,6 +266,8 @@ Network *parse_network_cfg(const char *filename, int batch, int quantized) {
             if (m) { l.mask = int_list(m); num = (int)l.mask.size(); }
             else { l.mask.resize(num); for (int i = 0; i < num; ++i) l.mask[i] = i; }
             l.n = num;
+            for (int mk : l.mask)   // the decoders read anchors[2 * mask[a]] (the reference would read out of bounds here)
+                if (mk < 0 || mk >= l.total) fatal_throw("yolo: mask entry " + std::to_string(mk) + " outside num=" + std::to_string(l.total));
             l.max_boxes = s.geti("max", 90);
             l.c = l.n * (l.classes + 4 + 1);
             l.out_w = l.w; l.out_h = l.h; l.out_c = l.c;
@@ -298,8 +308,7 @@ Network *parse_network_cfg(const char *filename, int batch, int quantized) {
 
 void set_batch(Network *net, int batch) {
     net->batch = batch;
-    net->engine[0].reset();
-    net->engine[1].reset();
+    drop_engines(net);
 }
 
 // load_weights_upto_cpu + load_convolutional_weights_cpu, additionally.c:3459-3529.  Like the reference, short
@@ -332,8 +341,7 @@ void load_weights_upto(Network *net, const char *filename, int cutoff) {
     }
     (void)r;
     fclose(fp);
-    net->engine[0].reset();
-    net->engine[1].reset();
+    drop_engines(net);
 }
 
 // yolov2_fuse_conv_batchnorm, additionally.c:67-109.  Expression order kept: b - (s*m)/(sqrt(v)+1e-6),
@@ -351,8 +359,7 @@ void fuse_conv_batchnorm(Network *net) {
         }
         l.batch_normalize = 0;
     }
-    net->engine[0].reset();
-    net->engine[1].reset();
+    drop_engines(net);
 }
 
 // calculate_binary_weights -> binary_align_weights -> binarize_weights / get_mean_array
@@ -373,8 +380,7 @@ void calculate_binary_weights(Network *net) {
         }
         l.has_mean_arr = true;
     }
-    net->engine[0].reset();
-    net->engine[1].reset();
+    drop_engines(net);
 }
 
 namespace {
@@ -424,8 +430,7 @@ void quantinization_and_get_multipliers(Network *net) {
         ++counter;
         l.has_int8 = true;
     }
-    net->engine[0].reset();
-    net->engine[1].reset();
+    drop_engines(net);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -456,6 +461,7 @@ int get_boxes(const Network *net, int b, int w, int h, float thresh, float nms, 
     std::vector<Det> dets;
     const int netw = net->w, neth = net->h;
     int classes = 0;
+    if (b < 0 || b >= net->batch) fatal_throw("get_boxes: batch item " + std::to_string(b) + " out of range");
     for (const Layer &l : net->layers) {
         if (l.type == YB_YOLO) {
             classes = l.classes;
@@ -495,9 +501,12 @@ int get_boxes(const Network *net, int b, int w, int h, float thresh, float nms, 
                     const float scale = p[p_index];
                     const int box_index = index * (l.classes + 5);
                     Det d;
-                    // get_region_box_cpu, yolov2_forward_network.c:653-661 (x,y through a double logistic)
-                    d.x = (float)((col + 1. / (1. + exp(-(double)p[box_index + 0]))) / l.w);
-                    d.y = (float)((row + 1. / (1. + exp(-(double)p[box_index + 1]))) / l.h);
+                    // get_region_box_cpu, yolov2_forward_network.c:653-661: logistic_activate computes in double and returns
+                    // float (additionally.h:85); the add and the divide are float operations
+                    const float lx = (float)(1. / (1. + exp(-(double)p[box_index + 0])));
+                    const float ly = (float)(1. / (1. + exp(-(double)p[box_index + 1])));
+                    d.x = (col + lx) / l.w;
+                    d.y = (row + ly) / l.h;
                     d.w = expf(p[box_index + 2]) * l.anchors[2 * n] / l.w;
                     d.h = expf(p[box_index + 3]) * l.anchors[2 * n + 1] / l.h;
                     d.objectness = 1;

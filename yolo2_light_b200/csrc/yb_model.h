@@ -65,6 +65,7 @@ void fuse_conv_batchnorm(Network *net);
 void calculate_binary_weights(Network *net);
 void quantinization_and_get_multipliers(Network *net);
 void set_batch(Network *net, int batch);
+void drop_engines(Network *net);   // resets both engines AND the host output pointers they own
 int get_boxes(const Network *net, int b, int w, int h, float thresh, float nms, int relative, int letter,
               float *out, int max_rows);
 
