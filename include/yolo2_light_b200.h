@@ -154,6 +154,20 @@ int    yb_network_fetch_input(yb_network *net, int quantized, float *dst);
 int yb_network_submit(yb_network *net, const float *input, int quantized);
 int yb_network_collect(yb_network *net, int ticket, int quantized);
 
+/* The serving loop of the reference app (src/main.c:188-229: load_image + resize_image, network_predict*, get_network_boxes,
+ * do_nms_sort) as ONE pipelined call per batch: yb_network_submit_u8 enqueues the H2D of net.batch 8-bit HWC frames (all
+ * w x h) and the reference's bilinear resize on a copy stream, the forward on the compute stream and the decode + NMS of the
+ * whole batch (the arithmetic of yb_network_detect) on a side stream where it runs under the NEXT batch's forward; it returns
+ * a ticket at once.  yb_network_collect_detections blocks until that batch is decoded and copies back exactly its candidate
+ * rows: *rows = pinned float[batch][max_rows][5 + classes] owned by the library (valid until the ticket's slot is reused, i.e.
+ * for the next 2 submits), *counts = int[batch] candidates per image before the max_rows cap (max_rows <= 16384),
+ * *d2h_bytes (optional) = bytes that crossed PCIe for this ticket.  Returns 5 + classes, or -1.  Up to 3 batches in flight.
+ * Per batch of 16 608x608 frames that is 17.7 MB in and < 1 MB out instead of 71 MB in / 124 MB out for the raw tensors. */
+int yb_network_submit_u8(yb_network *net, const unsigned char *images_hwc, int w, int h, int quantized, float thresh,
+                         float nms, int relative, int letter, int max_rows);
+int yb_network_collect_detections(yb_network *net, int ticket, int quantized, const float **rows, const int **counts,
+                                  size_t *d2h_bytes);
+
 /* Host output (NCHW for yolo, HWC-flattened for region, as the reference lays them out) of layer i after a
  * predict call; only YOLO/REGION layers (and the last layer) are kept on the host. */
 const float *yb_network_layer_output(const yb_network *net, int i, int *count);
@@ -173,6 +187,21 @@ int yb_network_fetch_layer(yb_network *net, int i, int quantized, float *dst);
  * Runs conv layer `i` of net alone on `input` (host NCHW, batch*c*h*w) and writes host NCHW `output`
  * (batch*n*out_h*out_w).  variant: 0 = as yb_network_predict would run it, 1 = as the quantized rule would. */
 int yb_forward_convolutional_layer(yb_network *net, int i, int variant, const float *input, float *output);
+
+/* ---- multi-GPU batch extension (SURVEY 8b "Batch extension", 8e) ------------------------------------------------------
+ * The reference runs one image per call on one device (src/main.c:199-219, cuda_set_device src/gpu.cu:97-102).  From the same
+ * plain-C host program -- one process, no Python, no launcher -- yb_network_predict_batch runs `nimg` images (host NCHW float,
+ * nimg * c*h*w) through `ngpus` replicas of the engine: contiguous shards of net.batch whole images go round-robin to the
+ * replicas (pipelined per GPU like yb_network_submit), the prepared weight arena is built on the first device and reaches the
+ * others by ONE ncclBroadcast at the first call (NCCL is bound at run time; without it, or for a device list with repeats,
+ * peer copies -- yb_network_replication() says which), and there is no other communication.  A partial last shard is padded
+ * with zero images whose results are dropped.  Results: yb_network_batch_output(net, i, &per_image) = host float[nimg][per_image]
+ * for every YOLO / REGION layer and the last layer, image k bit-identical to what yb_network_predict returns for it on one GPU.
+ * yb_network_set_devices chooses the devices (default 0 .. ngpus-1; repeats allowed: several replicas on one GPU). */
+int yb_network_set_devices(yb_network *net, const int *devices, int ndev);
+int yb_network_predict_batch(yb_network *net, const float *images, int nimg, int ngpus, int quantized);
+const float *yb_network_batch_output(const yb_network *net, int i, int *per_image);
+const char *yb_network_replication(const yb_network *net);   /* "nccl" | "peer-copy" | "single" | "" (not replicated yet) */
 
 /* Weight arena of the engine (all prepared device-side weights in one allocation) -- what a multi-GPU launcher
  * broadcasts once at init (one process per GPU; the harness uses torch.distributed/NCCL on this pointer).
@@ -219,7 +248,7 @@ int yb_get_network_boxes(const yb_network *net, int b, int w, int h, float thres
  * only).  rows: host float[batch][max_rows][5 + classes] = {x, y, w, h, objectness, prob[classes]} in the reference's
  * candidate order (layer, cell, anchor); suppressed / below-threshold class entries are 0 like the reference leaves
  * them.  counts[b] = number of candidates of image b; when it exceeds max_rows only the first max_rows candidates were
- * decoded and took part in the NMS (the reference has no cap: size max_rows accordingly, <= 8192).
+ * decoded and took part in the NMS (the reference has no cap: size max_rows accordingly, <= 16384).
  * Returns the row length 5 + classes, or -1. */
 int yb_network_detect(yb_network *net, int quantized, int w, int h, float thresh, float nms, int relative, int letter,
                       float *rows, int max_rows, int *counts);

@@ -7,6 +7,10 @@
  *
  *     float *network_predict_b200(network net, float *input);
  *     float *network_predict_b200_quantized(network net, float *input);
+ *     void   forward_convolutional_layer_b200(layer l, network_state state);      (slot of forward_convolutional_layer_cpu,
+ *     void   forward_convolutional_layer_b200_q(layer l, network_state state);     additionally.h:925 / ..._q, :927: by-value layer)
+ *     float *network_predict_b200_batch(network net, float *images, int nimg, int ngpus, int quantized);   (additive: many
+ *                                                 images over the GPUs of the box from this one C process)
  *     detection *get_network_boxes_nms_b200(network *net, int w, int h, float thresh, float nms, int relative, int *num,
  *                                           int letter);      (optional: decode + NMS on the device)
  *
@@ -26,8 +30,9 @@
 #include "additionally.h"
 #include "yolo2_light_b200.h"
 
-#define YB_GLUE_MAX_NETS 8
-static struct { layer *key; int quantized; yb_network *h; } g_nets[YB_GLUE_MAX_NETS];
+#define YB_GLUE_MAX_NETS 16
+static struct { layer *key; int quantized; yb_network *h; unsigned long stamp; } g_nets[YB_GLUE_MAX_NETS];
+static unsigned long g_stamp;   /* which handle of a net ran last: the decode must read THAT engine's tensors */
 
 static yb_network *glue_build(network net, int quantized)
 {
@@ -64,17 +69,25 @@ static yb_network *glue_build(network net, int quantized)
     return h;
 }
 
+static yb_network *glue_handle(network net, int quantized)
+{
+    int k;
+    for (k = 0; k < YB_GLUE_MAX_NETS; ++k)
+        if (g_nets[k].h && g_nets[k].key == net.layers && g_nets[k].quantized == quantized) { g_nets[k].stamp = ++g_stamp; return g_nets[k].h; }
+    for (k = 0; k < YB_GLUE_MAX_NETS; ++k)
+        if (!g_nets[k].h) {
+            g_nets[k].h = glue_build(net, quantized);
+            g_nets[k].key = net.layers; g_nets[k].quantized = quantized; g_nets[k].stamp = ++g_stamp;
+            return g_nets[k].h;
+        }
+    fprintf(stderr, "yolo2_light_b200 glue: more than %d (network, rule) pairs -- raise YB_GLUE_MAX_NETS\n", YB_GLUE_MAX_NETS);
+    exit(1);   /* the reference's error convention: message + exit */
+}
+
 static float *glue_predict(network net, float *input, int quantized)
 {
-    int k, i;
-    yb_network *h = NULL;
-    for (k = 0; k < YB_GLUE_MAX_NETS; ++k)
-        if (g_nets[k].h && g_nets[k].key == net.layers && g_nets[k].quantized == quantized) h = g_nets[k].h;
-    if (!h) {
-        h = glue_build(net, quantized);
-        for (k = 0; k < YB_GLUE_MAX_NETS; ++k)
-            if (!g_nets[k].h) { g_nets[k].key = net.layers; g_nets[k].quantized = quantized; g_nets[k].h = h; break; }
-    }
+    int i;
+    yb_network *h = glue_handle(net, quantized);
     if (quantized) yb_network_predict_quantized(h, input);
     else yb_network_predict(h, input);
     /* what get_network_boxes reads (additionally.c:4391-4398): host l.output of every YOLO / REGION layer */
@@ -90,12 +103,12 @@ static float *glue_predict(network net, float *input, int quantized)
     return net.layers[i].output;
 }
 
-static yb_network *glue_find(network *net)
+static int glue_find(network *net)   /* table slot of the handle of `net` that predicted last, or -1 */
 {
-    int k;
+    int k, best = -1;
     for (k = 0; k < YB_GLUE_MAX_NETS; ++k)
-        if (g_nets[k].h && g_nets[k].key == net->layers) return g_nets[k].h;
-    return NULL;
+        if (g_nets[k].h && g_nets[k].key == net->layers && (best < 0 || g_nets[k].stamp > g_nets[best].stamp)) best = k;
+    return best;
 }
 
 /*
@@ -107,14 +120,15 @@ static yb_network *glue_find(network *net)
  */
 detection *get_network_boxes_nms_b200(network *net, int w, int h, float thresh, float nms, int relative, int *num, int letter)
 {
-    yb_network *hnd = glue_find(net);
+    const int slot = glue_find(net);
+    yb_network *hnd;
     layer l = net->layers[net->n - 1];
     const int classes = l.classes, stride = 5 + classes, cap = 8192;
     float *rows;
-    int *counts, n, i, quantized = 0, k;
+    int *counts, n, i, quantized;
     detection *dets;
-    if (!hnd) { fprintf(stderr, "get_network_boxes_nms_b200: call network_predict_b200 first\n"); exit(1); }
-    for (k = 0; k < YB_GLUE_MAX_NETS; ++k) if (g_nets[k].h == hnd) quantized = g_nets[k].quantized;
+    if (slot < 0) { fprintf(stderr, "get_network_boxes_nms_b200: call network_predict_b200 first\n"); exit(1); }
+    hnd = g_nets[slot].h; quantized = g_nets[slot].quantized;
     rows = (float *)malloc(sizeof(float) * (size_t)net->batch * cap * stride);
     counts = (int *)calloc(net->batch, sizeof(int));
     if (yb_network_detect(hnd, quantized, w, h, thresh, nms, relative, letter, rows, cap, counts) != stride) {
@@ -133,6 +147,51 @@ detection *get_network_boxes_nms_b200(network *net, int w, int h, float thresh, 
     if (num) *num = n;
     free(rows); free(counts);
     return dets;
+}
+
+/*
+ * Slot of forward_convolutional_layer_cpu(layer l, network_state state) (src/additionally.h:925, yolov2_forward_network.c:30)
+ * and of forward_convolutional_layer_q (src/yolov2_forward_network_quantized.c:527): same by-value signature, reads
+ * state.input (host, l.batch * l.c*l.h*l.w floats), writes the layer's host l.output.  The FP32 / XNOR choice follows l.xnor
+ * like the reference; the _q form is the INT8 variant.  One single-layer engine per (layer, variant) is kept, keyed by the
+ * layer's weight pointer.
+ */
+#define YB_GLUE_MAX_LAYERS 512
+static struct { float *key; int variant; yb_network *h; } g_layers[YB_GLUE_MAX_LAYERS];
+
+static void glue_forward_conv(layer l, network_state state, int variant)
+{
+    int k;
+    yb_network *h = NULL;
+    if (l.type != CONVOLUTIONAL) { fprintf(stderr, "forward_convolutional_layer_b200: not a convolutional layer\n"); exit(1); }
+    for (k = 0; k < YB_GLUE_MAX_LAYERS && g_layers[k].h; ++k)
+        if (g_layers[k].key == l.weights && g_layers[k].variant == variant) { h = g_layers[k].h; break; }
+    if (!h) {
+        network one;
+        if (k == YB_GLUE_MAX_LAYERS) { fprintf(stderr, "forward_convolutional_layer_b200: layer table full\n"); exit(1); }
+        memset(&one, 0, sizeof(one));
+        one.n = 1; one.layers = &l; one.batch = l.batch; one.h = l.h; one.w = l.w; one.c = l.c; one.gpu_index = state.net.layers ? state.net.gpu_index : -1;
+        h = glue_build(one, variant);
+        if (variant) yb_network_set_option(h, "q_index_offset", 1);   /* the `i >= 1` half of the INT8 rule lives in the caller's loop */
+        g_layers[k].key = l.weights; g_layers[k].variant = variant; g_layers[k].h = h;
+    }
+    yb_forward_convolutional_layer(h, 0, variant, state.input, l.output);
+}
+void forward_convolutional_layer_b200(layer l, network_state state) { glue_forward_conv(l, state, 0); }
+void forward_convolutional_layer_b200_q(layer l, network_state state) { glue_forward_conv(l, state, 1); }
+
+/*
+ * Batch extension: `nimg` images (host NCHW float) over `ngpus` GPUs from this one process; weights are built on
+ * the first device and broadcast once.  Afterwards *per-image* results are read with yb_network_batch_output through the
+ * handle returned by network_b200_handle (the reference's layers hold room for net.batch images only).  Returns the last
+ * layer's results, nimg x outputs floats.
+ */
+yb_network *network_b200_handle(network net, int quantized) { return glue_handle(net, quantized); }
+float *network_predict_b200_batch(network net, float *images, int nimg, int ngpus, int quantized)
+{
+    yb_network *h = glue_handle(net, quantized);
+    if (yb_network_predict_batch(h, images, nimg, ngpus, quantized) != 0) { fprintf(stderr, "network_predict_b200_batch: %s\n", yb_last_error()); exit(1); }
+    return (float *)yb_network_batch_output(h, net.n - 1, NULL);
 }
 
 float *network_predict_b200(network net, float *input) { return glue_predict(net, input, 0); }

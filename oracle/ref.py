@@ -125,6 +125,30 @@ class RefNet:
         self.lib.refh_predict_b200(self.h, x.ctypes.data_as(C.c_void_p))
         return self.output(self.n - 1)
 
+    def forward_conv_b200(self, i: int, x: np.ndarray, use_q_rule: Optional[bool] = None) -> np.ndarray:
+        """forward_convolutional_layer_b200[_q](layer l, network_state state) of the glue (kind='dropin'): the reference's
+        by-value per-layer call shape served by the engine; the result lands in the reference layer's host l.output."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        q = self.quantized if use_q_rule is None else int(use_q_rule)
+        self.lib.refh_forward_conv_b200.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        self.lib.refh_forward_conv_b200(self.h, i, x.ctypes.data_as(C.c_void_p), q)
+        return self.output(i)
+
+    def predict_b200_batch(self, x: np.ndarray, ngpus: int) -> np.ndarray:
+        """network_predict_b200_batch of the glue: x = float32[nimg, c, h, w]; returns the last layer [nimg, outputs]."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        nimg = x.shape[0]
+        self.lib.refh_predict_b200_batch.restype = C.POINTER(C.c_float)
+        self.lib.refh_predict_b200_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        p = self.lib.refh_predict_b200_batch(self.h, x.ctypes.data_as(C.c_void_p), nimg, ngpus)
+        return np.ctypeslib.as_array(p, shape=(nimg, self.layers[-1]["outputs"])).copy()
+
+    def time_predict_b200(self, x: np.ndarray, reps: int, decode: bool = False, thresh: float = 0.24, nms: float = 0.45) -> float:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        self.lib.refh_time_predict_b200.restype = C.c_double
+        self.lib.refh_time_predict_b200.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float]
+        return float(self.lib.refh_time_predict_b200(self.h, x.ctypes.data_as(C.c_void_p), reps, int(decode), thresh, nms))
+
     def forward_layer(self, i: int, x: np.ndarray, use_q_rule: Optional[bool] = None) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=np.float32)
         q = self.quantized if use_q_rule is None else int(use_q_rule)

@@ -278,8 +278,46 @@ float *refh_predict_b200(refh *h, float *input)
 {
     return h->quantized ? network_predict_b200_quantized(h->net, input) : network_predict_b200(h->net, input);
 }
-/* the glue's device-side decode + NMS, reported in refh_get_boxes' row format */
+/* the reference's per-layer call shape (by-value layer + network_state) served by the engine: the conv of layer i alone */
+void forward_convolutional_layer_b200(layer l, network_state state);
+void forward_convolutional_layer_b200_q(layer l, network_state state);
+void refh_forward_conv_b200(refh *h, int i, float *input, int use_q_rule)
+{
+    network_state state;
+    memset(&state, 0, sizeof(state));
+    state.net = h->net;
+    state.index = i;
+    state.input = input;
+    state.workspace = h->net.workspace;
+    layer l = h->net.layers[i];
+    if (use_q_rule && i >= 1 && l.activation != LINEAR) forward_convolutional_layer_b200_q(l, state);   /* the loop's rule, :1036 */
+    else forward_convolutional_layer_b200(l, state);
+}
+/* batch extension: nimg images over ngpus GPUs from this C process; returns the last layer's nimg x outputs floats */
+float *network_predict_b200_batch(network net, float *images, int nimg, int ngpus, int quantized);
+float *refh_predict_b200_batch(refh *h, float *images, int nimg, int ngpus)
+{
+    return network_predict_b200_batch(h->net, images, nimg, ngpus, h->quantized);
+}
+/* wall-clock seconds per call of the drop-in pair predict + (optionally) device decode, as main.c:199-229 would run it */
 detection *get_network_boxes_nms_b200(network *net, int w, int h, float thresh, float nms, int relative, int *num, int letter);
+double refh_time_predict_b200(refh *h, float *input, int reps, int decode, float thresh, float nms)
+{
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int r = 0; r < reps; ++r) {
+        if (h->quantized) network_predict_b200_quantized(h->net, input);
+        else network_predict_b200(h->net, input);
+        if (decode) {
+            int nboxes = 0;
+            detection *dets = get_network_boxes_nms_b200(&h->net, h->net.w, h->net.h, thresh, nms, 1, &nboxes, 0);
+            free_detections(dets, nboxes);
+        }
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    return ((t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec)) / (reps > 0 ? reps : 1);
+}
+/* the glue's device-side decode + NMS, reported in refh_get_boxes' row format */
 int refh_get_boxes_b200(refh *h, int w, int hgt, float thresh, float nms, float *out, int max_out)
 {
     int nboxes = 0, k, c;

@@ -94,6 +94,12 @@ def lib():
         "yb_network_input_histogram": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp]),
         "yb_map_evaluate": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_float, C.c_float, vp, vp, vp]),
         "yb_network_detect": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, vp, C.c_int, vp]),
+        "yb_network_submit_u8": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int]),
+        "yb_network_collect_detections": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(fp), C.POINTER(ip), C.POINTER(C.c_size_t)]),
+        "yb_network_set_devices": (C.c_int, [vp, ip, C.c_int]),
+        "yb_network_predict_batch": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int]),
+        "yb_network_batch_output": (fp, [vp, C.c_int, ip]),
+        "yb_network_replication": (C.c_char_p, [vp]),
         "yb_network_predict": (fp, [vp, vp]),
         "yb_network_predict_quantized": (fp, [vp, vp]),
         "yb_network_predict_image_u8": (fp, [vp, vp, C.c_int, C.c_int, C.c_int]),
@@ -136,7 +142,8 @@ EXPORTED_SYMBOLS = [
     "yb_network_predict_image_u8", "yb_network_fetch_input", "yb_network_submit", "yb_network_collect", "yb_network_layer_output", "yb_network_forward_device", "yb_network_sync_outputs", "yb_network_fetch_layer",
     "yb_network_fetch_counts", "yb_forward_convolutional_layer", "yb_network_weight_arena",
     "yb_network_last_launches", "yb_network_profile", "yb_op_kind_name", "yb_get_network_boxes", "yb_alloc_pinned",
-    "yb_free_pinned",
+    "yb_free_pinned", "yb_network_submit_u8", "yb_network_collect_detections", "yb_network_set_devices",
+    "yb_network_predict_batch", "yb_network_batch_output", "yb_network_replication",
 ]
 
 
@@ -274,6 +281,57 @@ class Network:
         _check(lib().yb_network_collect(self._h, ticket, int(quantized)) == 0)
         getattr(self, "_inflight", {}).pop(ticket, None)
         return self.detection_outputs()
+
+    def submit_u8(self, images_hwc: np.ndarray, thresh: float, nms: float = 0.45, relative: int = 1, letter: int = 0,
+                  max_rows: int = 2048, quantized: bool = False) -> int:
+        """Pipelined u8 frames -> detections (``yb_network_submit_u8``): images_hwc uint8 [batch, h, w, c]."""
+        x = images_hwc if (isinstance(images_hwc, np.ndarray) and images_hwc.dtype == np.uint8 and images_hwc.flags.c_contiguous) \
+            else np.ascontiguousarray(images_hwc, dtype=np.uint8)
+        if x.ndim != 4 or x.shape[0] != self.batch or x.shape[3] != self.c:
+            raise YbError("submit_u8: expected uint8 [batch, h, w, c]")
+        self._inflight = getattr(self, "_inflight", {})
+        t = lib().yb_network_submit_u8(self._h, x.ctypes.data_as(C.c_void_p), int(x.shape[2]), int(x.shape[1]), int(quantized),
+                                       thresh, nms, relative, letter, max_rows)
+        _check(t >= 0)
+        self._inflight[("u8", t)] = (x, max_rows)
+        return t
+
+    def collect_detections(self, ticket: int, quantized: bool = False, copy: bool = True):
+        """Returns (list of [n_b, 5 + classes] arrays, counts int32[batch], bytes moved device -> host)."""
+        rows, counts, moved = C.POINTER(C.c_float)(), C.POINTER(C.c_int)(), C.c_size_t()
+        stride = lib().yb_network_collect_detections(self._h, ticket, int(quantized), C.byref(rows), C.byref(counts), C.byref(moved))
+        _check(stride > 0)
+        _, max_rows = getattr(self, "_inflight", {}).pop(("u8", ticket), (None, None))
+        cnt = np.ctypeslib.as_array(counts, shape=(self.batch,)).copy()
+        if max_rows is None:
+            raise YbError("collect_detections: unknown ticket")
+        allrows = np.ctypeslib.as_array(rows, shape=(self.batch, max_rows, stride))
+        out = [allrows[b, :min(int(cnt[b]), max_rows)] for b in range(self.batch)]
+        if copy:
+            out = [o.copy() for o in out]
+        return out, cnt, int(moved.value)
+
+    def set_devices(self, devices) -> None:
+        arr = (C.c_int * len(devices))(*devices)
+        _check(lib().yb_network_set_devices(self._h, arr, len(devices)) == 0)
+
+    def predict_batch(self, images: np.ndarray, ngpus: int, quantized: bool = False) -> dict:
+        """``yb_network_predict_batch``: any number of images over `ngpus` engine replicas of this process."""
+        x = np.ascontiguousarray(images, dtype=np.float32)
+        nimg = x.shape[0]
+        if x.size != nimg * self.c * self.h * self.w:
+            raise YbError("predict_batch: wrong input size")
+        _check(lib().yb_network_predict_batch(self._h, x.ctypes.data_as(C.c_void_p), nimg, ngpus, int(quantized)) == 0)
+        out = {}
+        for i in range(self.n):
+            per = C.c_int()
+            p = lib().yb_network_batch_output(self._h, i, C.byref(per))
+            if p:
+                out[i] = _np(p, nimg * per.value, np.float32).reshape(nimg, -1).copy()
+        return out
+
+    def replication(self) -> str:
+        return lib().yb_network_replication(self._h).decode()
 
     def layer_output(self, i: int) -> np.ndarray:
         """Host output of a YOLO / REGION / last layer after predict (view on pinned memory; copy to keep)."""

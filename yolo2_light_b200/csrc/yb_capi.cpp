@@ -267,6 +267,23 @@ int yb_network_collect(yb_network *n, int ticket, int quantized) {
     YB_CATCH(-1)
 }
 
+int yb_network_submit_u8(yb_network *n, const unsigned char *images_hwc, int w, int h, int quantized, float thresh, float nms,
+                         int relative, int letter, int max_rows) {
+    YB_TRY
+    if (w <= 0 || h <= 0 || !images_hwc) fatal_throw("submit_u8: bad image");
+    Engine *e = get_engine(n, quantized);
+    const int t = engine_submit_u8(e, &n->net, images_hwc, w, h, thresh, nms, relative, letter, max_rows);
+    n->net.last_launches = engine_num_launches(e) + 5;   // + resize, count, emit, iou, nms
+    return t;
+    YB_CATCH(-1)
+}
+int yb_network_collect_detections(yb_network *n, int ticket, int quantized, const float **rows, const int **counts,
+                                  size_t *d2h_bytes) {
+    YB_TRY
+    return engine_collect_detections(get_engine(n, quantized), ticket, rows, counts, d2h_bytes);
+    YB_CATCH(-1)
+}
+
 float *yb_network_predict_image_u8(yb_network *n, const unsigned char *images_hwc, int w, int h, int quantized) {
     YB_TRY
     Network &net = n->net;
@@ -329,21 +346,126 @@ int yb_forward_convolutional_layer(yb_network *n, int i, int variant, const floa
     const Network &src = n->net;
     if (i < 0 || i >= (int)src.layers.size() || src.layers[i].type != YB_CONVOLUTIONAL)
         fatal_throw("yb_forward_convolutional_layer: not a convolutional layer");
-    yb_network tmp;
-    Network &t = tmp.net;
-    const Layer &l = src.layers[i];
-    t.batch = src.batch; t.h = l.h; t.w = l.w; t.c = l.c; t.inputs = l.h * l.w * l.c;
-    t.device = src.device; t.precision = src.precision; t.fuse = false;
-    t.q_index_offset = i;
-    t.layers.push_back(l);
-    t.layers[0].output = nullptr;
-    Engine *e = get_engine(&tmp, variant);
+    if (!input || !output) fatal_throw("yb_forward_convolutional_layer: null buffer");
+    const int key = 2 * i + (variant ? 1 : 0);
+    auto it = n->single.find(key);
+    if (it == n->single.end() || it->second->net.batch != src.batch || it->second->net.device != src.device ||
+        it->second->net.precision != src.precision) {
+        std::unique_ptr<yb_network> tmp(new yb_network());
+        Network &t = tmp->net;
+        const Layer &l = src.layers[i];
+        t.batch = src.batch; t.h = l.h; t.w = l.w; t.c = l.c; t.inputs = l.h * l.w * l.c;
+        t.device = src.device; t.precision = src.precision; t.fuse = false;
+        t.q_index_offset = i + src.q_index_offset;   // the `i >= 1` half of the INT8 rule
+        t.layers.push_back(l);
+        t.layers[0].output = nullptr; t.layers[0].output_count = 0;
+        it = n->single.insert_or_assign(key, std::move(tmp)).first;
+    }
+    yb_network *one = it->second.get();
+    Engine *e = get_engine(one, variant);
     engine_upload_input(e, input, nullptr);
     engine_forward(e, nullptr, nullptr);
-    engine_fetch_layer(e, &t, 0, output);
+    engine_fetch_layer(e, &one->net, 0, output);
     return 0;
     YB_CATCH(-1)
 }
+
+/* ---- multi-GPU batch extension (SURVEY 8b "Batch extension", 8e) ------------------------------------------------------- */
+int yb_network_set_devices(yb_network *n, const int *devices, int ndev) {
+    YB_TRY
+    if (ndev < 0 || (ndev > 0 && !devices)) fatal_throw("set_devices: bad arguments");
+    const int have = engine_device_count();
+    for (int k = 0; k < ndev; ++k)
+        if (devices[k] < 0 || devices[k] >= have) fatal_throw("set_devices: device " + std::to_string(devices[k]) + " does not exist");
+    n->devices.assign(devices, devices + ndev);
+    n->replicas[0].clear(); n->replicas[1].clear();
+    if (ndev > 0 && n->net.device != devices[0]) { n->net.device = devices[0]; drop_engines(&n->net); }
+    return 0;
+    YB_CATCH(-1)
+}
+
+static std::vector<Engine *> get_replicas(yb_network *n, int quantized, int ngpus) {
+    const int slot = quantized ? 1 : 0;
+    if (n->devices.empty() || (int)n->devices.size() < ngpus) {
+        const int have = engine_device_count();
+        if (ngpus > have) fatal_throw("predict_batch: " + std::to_string(ngpus) + " GPUs requested, " + std::to_string(have) + " visible");
+        n->devices.resize(ngpus);
+        for (int k = 0; k < ngpus; ++k) n->devices[k] = k;
+        n->replicas[0].clear(); n->replicas[1].clear();
+    }
+    if (n->net.device != n->devices[0]) { n->net.device = n->devices[0]; drop_engines(&n->net); n->replicas[0].clear(); n->replicas[1].clear(); }
+    const bool fresh0 = !n->net.engine[slot];
+    Engine *e0 = get_engine(n, quantized);
+    if (fresh0) n->replicas[slot].clear();           // replica 0 was rebuilt: the others hold stale plans
+    std::vector<std::shared_ptr<Engine>> &reps = n->replicas[slot];
+    bool built = false;
+    while ((int)reps.size() < ngpus - 1) {
+        EngineOptions opt;
+        opt.device = n->devices[reps.size() + 1];
+        opt.precision = n->net.precision; opt.qrule = quantized != 0; opt.upload = false;   // weights arrive by the broadcast
+        const char *nf = getenv("YB_NO_FUSE");
+        opt.fuse = !(nf && nf[0] == '1') && n->net.fuse;
+        opt.keep_counts = n->net.keep_counts; opt.ksplit = n->net.ksplit; opt.q_index_offset = n->net.q_index_offset;
+        reps.push_back(build_engine(&n->net, opt));
+        built = true;
+    }
+    std::vector<Engine *> all{e0};
+    for (int k = 0; k + 1 < ngpus; ++k) all.push_back(reps[k].get());
+    if (built) n->replication = engine_broadcast_arena(all);   // ONE collective, at init only
+    return all;
+}
+
+int yb_network_predict_batch(yb_network *n, const float *images, int nimg, int ngpus, int quantized) {
+    YB_TRY
+    Network &net = n->net;
+    if (!images || nimg <= 0 || ngpus <= 0) fatal_throw("predict_batch: bad arguments");
+    const std::vector<Engine *> reps = get_replicas(n, quantized, ngpus);
+    const int B = net.batch;
+    const size_t per_img = (size_t)net.c * net.h * net.w;
+    n->batch_out.assign(net.layers.size(), {});
+    for (size_t i = 0; i < net.layers.size(); ++i) {
+        const Layer &l = net.layers[i];
+        if (l.type == YB_YOLO || l.type == YB_REGION || i + 1 == net.layers.size()) n->batch_out[i].assign((size_t)nimg * l.outputs, 0.f);
+    }
+    n->batch_nimg = nimg;
+    struct Pending { int ticket, first, count; };
+    std::vector<std::vector<Pending>> q(ngpus);
+    std::vector<std::vector<float>> padded;          // partial last shards, kept alive until collected
+    std::vector<const float *> ptrs; std::vector<size_t> counts;
+    auto collect_oldest = [&](int g) {
+        const Pending p = q[g].front();
+        q[g].erase(q[g].begin());
+        engine_collect_ptrs(reps[g], p.ticket, ptrs, counts);
+        for (size_t i = 0; i < ptrs.size(); ++i) {
+            if (!ptrs[i] || n->batch_out[i].empty()) continue;
+            const size_t outs = (size_t)net.layers[i].outputs;
+            memcpy(n->batch_out[i].data() + (size_t)p.first * outs, ptrs[i], sizeof(float) * outs * p.count);
+        }
+    };
+    int shard = 0;
+    for (int first = 0; first < nimg; first += B, ++shard) {
+        const int g = shard % ngpus, cnt = std::min(B, nimg - first);
+        if (q[g].size() == 3) collect_oldest(g);
+        const float *src = images + (size_t)first * per_img;
+        if (cnt < B) {   // contiguous shards of whole images; the tail is padded with zero images whose results are dropped
+            padded.emplace_back((size_t)B * per_img, 0.f);
+            memcpy(padded.back().data(), src, sizeof(float) * per_img * cnt);
+            src = padded.back().data();
+        }
+        q[g].push_back(Pending{engine_submit(reps[g], src), first, cnt});
+    }
+    for (int g = 0; g < ngpus; ++g) while (!q[g].empty()) collect_oldest(g);
+    net.last_launches = engine_num_launches(reps[0]);
+    return 0;
+    YB_CATCH(-1)
+}
+
+const float *yb_network_batch_output(const yb_network *n, int i, int *per_image) {
+    if (i < 0 || i >= (int)n->batch_out.size() || n->batch_out[i].empty()) return nullptr;
+    if (per_image) *per_image = n->net.layers[i].outputs;
+    return n->batch_out[i].data();
+}
+const char *yb_network_replication(const yb_network *n) { return n->replication.c_str(); }
 
 int yb_network_weight_arena(yb_network *n, int quantized, int upload, void **d_ptr, size_t *bytes) {
     YB_TRY

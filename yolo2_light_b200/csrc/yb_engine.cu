@@ -8,6 +8,7 @@
 
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -76,8 +77,6 @@ struct Engine {
     bool graph_failed = false;
     std::vector<void *> tc_plans;      // opaque per-layer state of the tensor-core path (tensor maps)
     // device-side decode + NMS workspace (engine_detect), sized for det_cap rows per image
-    float *det_rows = nullptr; unsigned *det_mask = nullptr; int *det_blkcnt = nullptr, *det_counts = nullptr;
-    int det_cap = 0, det_stride = 0, det_nblk = 0;
     int n_tc = 0, n_ksplit = 0;
     float *ksplit_ws = nullptr; unsigned *ksplit_flags = nullptr;   // partial sums / flags of the K-split tail (yb_conv_tc.cu)
     std::function<void(const float *, cudaStream_t)> first_op;   // consumes the caller's NCHW images (pointer varies per call)
@@ -85,15 +84,25 @@ struct Engine {
     void *stem_plan = nullptr;
     unsigned char *d_u8 = nullptr; size_t u8_bytes = 0;   // staging of the caller's u8 images (device-side input pipeline)
     // ---- pipelined end-to-end path: H2D(k+1) | compute(k) | D2H(k-1) on three streams -----------------
+    struct DetWs {                      // decode + NMS workspace for `cap` candidate rows per image
+        float *rows = nullptr; unsigned *mask = nullptr; int *blkcnt = nullptr, *counts = nullptr;
+        int cap = 0, stride = 0, nblk = 0;
+    };
     struct Slot {
         float *d_in = nullptr;
         std::vector<float *> d_out, h_out;
-        cudaEvent_t ev_in = nullptr, ev_comp = nullptr, ev_done = nullptr;
+        cudaEvent_t ev_in = nullptr, ev_comp = nullptr, ev_done = nullptr, ev_det = nullptr;
         bool busy = false;
+        // device-side input pipeline + decode of the pipelined detection path (engine_submit_u8)
+        unsigned char *d_u8 = nullptr; size_t u8_bytes = 0;
+        DetWs det;
+        float *h_rows = nullptr; size_t h_rows_bytes = 0; int *h_counts = nullptr;
+        int mode = 0;                   // 0: raw tensors (engine_submit), 1: detections (engine_submit_u8)
     };
     std::vector<Slot> slots;
-    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_det = nullptr;
     int next_slot = 0;
+    DetWs det;                          // workspace of the synchronous engine_detect
     ~Engine();
 };
 
@@ -105,14 +114,22 @@ Engine::~Engine() {
     for (int32_t *p : d_counts) if (p) cudaFree(p);
     for (void *p : tc_plans) tc_free_plan(p);
     if (stem_plan) tc_stem_free_plan(stem_plan);
-    if (det_rows) cudaFree(det_rows);
-    if (det_mask) cudaFree(det_mask);
-    if (det_blkcnt) cudaFree(det_blkcnt);
-    if (det_counts) cudaFree(det_counts);
+    if (det.rows) cudaFree(det.rows);
+    if (det.mask) cudaFree(det.mask);
+    if (det.blkcnt) cudaFree(det.blkcnt);
+    if (det.counts) cudaFree(det.counts);
     if (ksplit_ws) cudaFree(ksplit_ws);
     if (ksplit_flags) cudaFree(ksplit_flags);
     if (d_u8) cudaFree(d_u8);
     for (Slot &sl : slots) {
+        if (sl.d_u8) cudaFree(sl.d_u8);
+        if (sl.det.rows) cudaFree(sl.det.rows);
+        if (sl.det.mask) cudaFree(sl.det.mask);
+        if (sl.det.blkcnt) cudaFree(sl.det.blkcnt);
+        if (sl.det.counts) cudaFree(sl.det.counts);
+        if (sl.h_rows) cudaFreeHost(sl.h_rows);
+        if (sl.h_counts) cudaFreeHost(sl.h_counts);
+        if (sl.ev_det) cudaEventDestroy(sl.ev_det);
         if (sl.d_in) cudaFree(sl.d_in);
         for (float *p : sl.d_out) if (p) cudaFree(p);
         for (float *p : sl.h_out) if (p) cudaFreeHost(p);
@@ -122,6 +139,7 @@ Engine::~Engine() {
     }
     if (s_in) cudaStreamDestroy(s_in);
     if (s_out) cudaStreamDestroy(s_out);
+    if (s_det) cudaStreamDestroy(s_det);
     if (act_arena) cudaFree(act_arena);
     if (w_arena) cudaFree(w_arena);
     if (d_input) cudaFree(d_input);
@@ -1005,7 +1023,9 @@ static void ensure_slots(Engine *e) {
         CUDA_OK(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
         CUDA_OK(cudaEventCreateWithFlags(&sl.ev_comp, cudaEventDisableTiming));
         CUDA_OK(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&sl.ev_det, cudaEventDisableTiming));
     }
+    CUDA_OK(cudaStreamCreateWithFlags(&e->s_det, cudaStreamNonBlocking));
 }
 
 // Enqueue one batch: H2D on the copy-in stream, forward on the compute stream, D2H on the copy-out stream.
@@ -1023,8 +1043,9 @@ int engine_submit(Engine *e, const float *host_input) {
     CUDA_OK(cudaEventRecord(sl.ev_in, e->s_in));
     CUDA_OK(cudaStreamWaitEvent(e->stream, sl.ev_in, 0));
     engine_forward(e, sl.d_in, e->stream);
-    // the previous D2H out of d_out[k] must have finished before it is overwritten
+    // the previous D2H out of d_out[k] (or decode of it) must have finished before it is overwritten
     CUDA_OK(cudaStreamWaitEvent(e->stream, sl.ev_done, 0));
+    CUDA_OK(cudaStreamWaitEvent(e->stream, sl.ev_det, 0));
     for (size_t i = 0; i < e->d_final.size(); ++i)
         if (e->d_final[i])
             CUDA_OK(cudaMemcpyAsync(sl.d_out[i], e->d_final[i], e->final_count[i] * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
@@ -1034,22 +1055,83 @@ int engine_submit(Engine *e, const float *host_input) {
         if (e->d_final[i])
             CUDA_OK(cudaMemcpyAsync(sl.h_out[i], sl.d_out[i], e->final_count[i] * sizeof(float), cudaMemcpyDeviceToHost, e->s_out));
     CUDA_OK(cudaEventRecord(sl.ev_done, e->s_out));
-    sl.busy = true;
+    sl.busy = true; sl.mode = 0;
     return k;
 }
 
-void engine_collect(Engine *e, Network *net, int ticket) {
-    if (ticket < 0 || ticket >= (int)e->slots.size() || !e->slots[ticket].busy) fatal_throw("collect: bad ticket");
+// ptrs[i] = pinned host copy of layer i's output for this ticket (nullptr where the layer has none); valid until the slot
+// is reused.  The form the multi-GPU batch call uses: several engines feed ONE host model.
+void engine_collect_ptrs(Engine *e, int ticket, std::vector<const float *> &ptrs, std::vector<size_t> &counts) {
+    if (ticket < 0 || ticket >= (int)e->slots.size() || !e->slots[ticket].busy || e->slots[ticket].mode != 0)
+        fatal_throw("collect: bad ticket");
     CUDA_OK(cudaSetDevice(e->opt.device));
     Engine::Slot &sl = e->slots[ticket];
     CUDA_OK(cudaEventSynchronize(sl.ev_done));
+    ptrs.assign(e->d_final.size(), nullptr);
+    counts.assign(e->d_final.size(), 0);
     for (size_t i = 0; i < e->d_final.size(); ++i) {
         if (!e->d_final[i]) continue;
-        net->layers[i].output = sl.h_out[i];
-        net->layers[i].output_count = e->final_count[i];
+        ptrs[i] = sl.h_out[i];
+        counts[i] = e->final_count[i];
     }
     sl.busy = false;
 }
+
+void engine_collect(Engine *e, Network *net, int ticket) {
+    std::vector<const float *> ptrs; std::vector<size_t> counts;
+    engine_collect_ptrs(e, ticket, ptrs, counts);
+    for (size_t i = 0; i < ptrs.size(); ++i) {
+        if (!ptrs[i]) continue;
+        net->layers[i].output = const_cast<float *>(ptrs[i]);
+        net->layers[i].output_count = counts[i];
+    }
+}
+
+// ---- weight replication across the GPUs of one process (ONE broadcast of the prepared arena at init) ---------
+// NCCL is bound at run time (dlopen): the library has no link-time dependency on it, and a host without NCCL -- or a device
+// list with repeats, which NCCL refuses -- falls back to peer copies out of replica 0.
+const char *engine_broadcast_arena(const std::vector<Engine *> &reps) {
+    if (reps.size() < 2) return "single";
+    const size_t bytes = reps[0]->w_bytes;
+    for (Engine *r : reps) if (r->w_bytes != bytes) fatal_throw("broadcast: replicas disagree on the arena size");
+    bool distinct = true;
+    for (size_t a = 0; a < reps.size(); ++a)
+        for (size_t b = a + 1; b < reps.size(); ++b) distinct &= reps[a]->opt.device != reps[b]->opt.device;
+    typedef int (*InitAllFn)(void **, int, const int *);
+    typedef int (*BcastFn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+    typedef int (*VoidFn)(void);
+    typedef int (*DestroyFn)(void *);
+    void *lib = (distinct && !getenv("YB_NO_NCCL")) ? dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL) : nullptr;
+    if (lib) {
+        InitAllFn init_all = (InitAllFn)dlsym(lib, "ncclCommInitAll");
+        BcastFn bcast = (BcastFn)dlsym(lib, "ncclBroadcast");
+        VoidFn gstart = (VoidFn)dlsym(lib, "ncclGroupStart"), gend = (VoidFn)dlsym(lib, "ncclGroupEnd");
+        DestroyFn destroy = (DestroyFn)dlsym(lib, "ncclCommDestroy");
+        if (init_all && bcast && gstart && gend && destroy) {
+            std::vector<void *> comms(reps.size(), nullptr);
+            std::vector<int> devs;
+            for (Engine *r : reps) devs.push_back(r->opt.device);
+            if (init_all(comms.data(), (int)reps.size(), devs.data()) == 0) {
+                int rc = gstart();
+                for (size_t k = 0; k < reps.size() && rc == 0; ++k) {
+                    CUDA_OK(cudaSetDevice(reps[k]->opt.device));
+                    rc = bcast(reps[k]->w_arena, reps[k]->w_arena, bytes, /*ncclChar*/ 0, /*root*/ 0, comms[k], reps[k]->stream);
+                }
+                rc |= gend();
+                for (Engine *r : reps) { CUDA_OK(cudaSetDevice(r->opt.device)); CUDA_OK(cudaStreamSynchronize(r->stream)); }
+                for (void *c : comms) if (c) destroy(c);
+                if (rc == 0) return "nccl";
+            }
+        }
+    }
+    for (size_t k = 1; k < reps.size(); ++k) {
+        CUDA_OK(cudaSetDevice(reps[0]->opt.device));
+        CUDA_OK(cudaMemcpyPeer(reps[k]->w_arena, reps[k]->opt.device, reps[0]->w_arena, reps[0]->opt.device, bytes));
+    }
+    CUDA_OK(cudaDeviceSynchronize());
+    return "peer-copy";
+}
+int engine_device_count() { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
 
 void engine_fetch_layer(Engine *e, Network *net, int layer, float *dst) {
     CUDA_OK(cudaSetDevice(e->opt.device));
@@ -1112,23 +1194,25 @@ void engine_input_histogram(Engine *e, Network *net, int layer, int img, float b
     cudaFree(d_hist);
 }
 
-// Batched decode + NMS on the device (yb_detect.cuh).  rows: [batch][max_rows][5 + classes]; counts[b] = candidates of
-// image b before the max_rows cap.  Returns 5 + classes.
-int engine_detect(Engine *e, Network *net, int w, int h, float thresh, float nms, int relative, int letter,
-                  float *rows, int max_rows, int *counts) {
-    CUDA_OK(cudaSetDevice(e->opt.device));
-    if (max_rows <= 0 || max_rows > 8192) fatal_throw("detect: max_rows must be in 1..8192");
+// ---- batched decode + NMS on the device (yb_detect.cuh) ---------------------------------------------------------
+static constexpr int DET_MAX_ROWS = 16384;   // the per-(class, image) sort lives in shared memory: 8 B per (power-of-two) row
+
+static DetParams det_params(Engine *e, Network *net, const std::vector<float *> &finals, int w, int h, float thresh, float nms,
+                            int relative, int letter, int max_rows) {
+    if (max_rows <= 0 || max_rows > DET_MAX_ROWS) fatal_throw("detect: max_rows must be in 1.." + std::to_string(DET_MAX_ROWS));
     DetParams P{};
     int total = 0;
     for (size_t i = 0; i < net->layers.size(); ++i) {
         const Layer &l = net->layers[i];
         if (l.type != YB_YOLO && l.type != YB_REGION) continue;
-        if (!e->d_final[i]) fatal_throw("detect: detection layer has no device output");
+        if (!finals[i]) fatal_throw("detect: detection layer has no device output");
         if (P.nl == DET_MAX_LAYERS) fatal_throw("detect: too many detection layers");
         if (l.n > DET_MAX_ANCHORS) fatal_throw("detect: too many anchors per layer");
         if (P.nl && l.classes != P.classes) fatal_throw("detect: detection layers disagree on the class count");
+        if ((l.type == YB_YOLO && (int)l.mask.size() < l.n) || (int)l.anchors.size() < 2 * l.n)
+            fatal_throw("detect: detection layer without mask / anchors");
         DetLayer &d = P.L[P.nl++];
-        d.p = e->d_final[i]; d.type = l.type; d.w = l.w; d.h = l.h; d.n = l.n; d.classes = l.classes; d.outputs = l.outputs;
+        d.p = finals[i]; d.type = l.type; d.w = l.w; d.h = l.h; d.n = l.n; d.classes = l.classes; d.outputs = l.outputs;
         d.base = total; d.nbox = l.w * l.h * l.n; total += d.nbox;
         for (int a = 0; a < l.n; ++a) {
             const int k = (l.type == YB_YOLO) ? l.mask[a] : a;
@@ -1144,45 +1228,144 @@ int engine_detect(Engine *e, Network *net, int w, int h, float thresh, float nms
         else { P.new_h = net->h; P.new_w = (w * net->h) / h; }
     }
     P.thresh = thresh; P.nms = nms; P.max_rows = max_rows; P.nblk = (total + 255) / 256;
-    const int B = e->batch, stride = 5 + P.classes, words = (max_rows + 31) / 32;
-    if (e->det_cap != max_rows || e->det_stride != stride || e->det_nblk < P.nblk) {   // pitch == cap == max_rows: the NMS
-                                                                                           // sees exactly the rows the caller asked for
-        if (e->det_rows) cudaFree(e->det_rows);
-        if (e->det_mask) cudaFree(e->det_mask);
-        if (e->det_blkcnt) cudaFree(e->det_blkcnt);
-        if (e->det_counts) cudaFree(e->det_counts);
-        CUDA_OK(cudaMalloc(&e->det_rows, (size_t)B * max_rows * stride * sizeof(float)));
-        CUDA_OK(cudaMalloc(&e->det_mask, (size_t)B * max_rows * words * sizeof(unsigned)));
-        CUDA_OK(cudaMalloc(&e->det_blkcnt, (size_t)B * P.nblk * sizeof(int)));
-        CUDA_OK(cudaMalloc(&e->det_counts, (size_t)B * sizeof(int)));
-        e->det_cap = max_rows; e->det_stride = stride; e->det_nblk = P.nblk;
-    }
-    P.max_rows = e->det_cap;   // row pitch of the workspace
-    const int cap = e->det_cap, capw = (cap + 31) / 32;
+    (void)e;
+    return P;
+}
+
+static void det_ws_ensure(Engine::DetWs &ws, int B, const DetParams &P) {
+    const int stride = 5 + P.classes, words = (P.max_rows + 31) / 32;
+    if (ws.cap == P.max_rows && ws.stride == stride && ws.nblk >= P.nblk) return;   // pitch == cap == max_rows: the NMS sees
+                                                                                    // exactly the rows the caller asked for
+    if (ws.rows) cudaFree(ws.rows);
+    if (ws.mask) cudaFree(ws.mask);
+    if (ws.blkcnt) cudaFree(ws.blkcnt);
+    if (ws.counts) cudaFree(ws.counts);
+    CUDA_OK(cudaMalloc(&ws.rows, (size_t)B * P.max_rows * stride * sizeof(float)));
+    CUDA_OK(cudaMalloc(&ws.mask, (size_t)B * P.max_rows * words * sizeof(unsigned)));
+    CUDA_OK(cudaMalloc(&ws.blkcnt, (size_t)B * P.nblk * sizeof(int)));
+    CUDA_OK(cudaMalloc(&ws.counts, (size_t)B * sizeof(int)));
+    ws.cap = P.max_rows; ws.stride = stride; ws.nblk = P.nblk;
+}
+
+static void det_launch_count_emit(const DetParams &P, Engine::DetWs &ws, int B, cudaStream_t s) {
+    k_det_count<<<dim3((unsigned)P.nblk, (unsigned)B), 256, 0, s>>>(P, ws.blkcnt);
+    k_det_emit<<<dim3((unsigned)P.nblk, (unsigned)B), 256, 0, s>>>(P, ws.blkcnt, ws.rows, ws.counts);
+}
+// nmax: upper bound of the candidates of any image (the kernels read the true counts on the device and idle beyond them)
+static void det_launch_nms(const DetParams &P, Engine::DetWs &ws, int B, int nmax, cudaStream_t s) {
+    if (!(P.nms > 0.f) || nmax <= 0) return;
+    const int capw = (ws.cap + 31) / 32;
+    k_det_iou<<<dim3((unsigned)((capw + 127) / 128), (unsigned)nmax, (unsigned)B), 128, 0, s>>>(P, ws.rows, ws.counts, ws.mask);
+    int P2 = 1; while (P2 < nmax) P2 <<= 1;
+    const size_t smem = (size_t)P2 * 8 + (size_t)capw * 4;
+    if (smem > 48 * 1024)
+        CUDA_OK(cudaFuncSetAttribute(k_det_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_det_nms<<<dim3((unsigned)P.classes, (unsigned)B), 256, smem, s>>>(P, ws.rows, ws.counts, ws.mask, P2);
+}
+
+// Synchronous form.  rows: [batch][max_rows][5 + classes]; counts[b] = candidates of image b before the max_rows cap.
+// Returns 5 + classes.
+int engine_detect(Engine *e, Network *net, int w, int h, float thresh, float nms, int relative, int letter,
+                  float *rows, int max_rows, int *counts) {
+    CUDA_OK(cudaSetDevice(e->opt.device));
+    const DetParams P = det_params(e, net, e->d_final, w, h, thresh, nms, relative, letter, max_rows);
+    const int B = e->batch, stride = 5 + P.classes;
+    det_ws_ensure(e->det, B, P);
     cudaStream_t s = e->stream;
-    k_det_count<<<dim3((unsigned)P.nblk, (unsigned)B), 256, 0, s>>>(P, e->det_blkcnt);
-    k_det_emit<<<dim3((unsigned)P.nblk, (unsigned)B), 256, 0, s>>>(P, e->det_blkcnt, e->det_rows, e->det_counts);
+    det_launch_count_emit(P, e->det, B, s);
     std::vector<int> hc(B);
-    CUDA_OK(cudaMemcpyAsync(hc.data(), e->det_counts, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(hc.data(), e->det.counts, B * sizeof(int), cudaMemcpyDeviceToHost, s));
     CUDA_OK(cudaStreamSynchronize(s));
     int nmax = 0;
-    for (int b = 0; b < B; ++b) { counts[b] = hc[b]; nmax = std::max(nmax, std::min(hc[b], cap)); }
-    if (nms > 0.f && nmax > 0) {
-        k_det_iou<<<dim3((unsigned)((capw + 127) / 128), (unsigned)nmax, (unsigned)B), 128, 0, s>>>(P, e->det_rows, e->det_counts, e->det_mask);
-        int P2 = 1; while (P2 < nmax) P2 <<= 1;
-        const size_t smem = (size_t)P2 * 8 + (size_t)capw * 4;
-        if (smem > 48 * 1024)
-            CUDA_OK(cudaFuncSetAttribute(k_det_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_det_nms<<<dim3((unsigned)P.classes, (unsigned)B), 256, smem, s>>>(P, e->det_rows, e->det_counts, e->det_mask, P2);
-    }
+    for (int b = 0; b < B; ++b) { counts[b] = hc[b]; nmax = std::max(nmax, std::min(hc[b], max_rows)); }
+    det_launch_nms(P, e->det, B, nmax, s);
     for (int b = 0; b < B; ++b) {
-        const int n = std::min(hc[b], std::min(cap, max_rows));
+        const int n = std::min(hc[b], max_rows);
         if (n > 0)
-            CUDA_OK(cudaMemcpyAsync(rows + (size_t)b * max_rows * stride, e->det_rows + (size_t)b * cap * stride,
+            CUDA_OK(cudaMemcpyAsync(rows + (size_t)b * max_rows * stride, e->det.rows + (size_t)b * max_rows * stride,
                                     (size_t)n * stride * sizeof(float), cudaMemcpyDeviceToHost, s));
     }
     CUDA_OK(cudaStreamSynchronize(s));
     CUDA_OK(cudaGetLastError());
+    return stride;
+}
+
+// ---- pipelined detection path (SURVEY 8f rows 1 + 2 in the serving loop) -----------------------------------------
+// One call enqueues, for one batch of 8-bit frames: H2D of the frames + the reference's resize on the copy-in stream, the
+// forward on the compute stream, decode + NMS on a side stream (under the forward of the NEXT batch), and returns a ticket.
+// engine_collect_detections waits for that batch and copies back exactly the candidate rows.  Host traffic per batch: the
+// u8 frames in (a quarter of the float images), counts + rows out (a few hundred KB instead of the 124 MB of yolo tensors).
+int engine_submit_u8(Engine *e, Network *net, const unsigned char *host_u8, int w, int h, float thresh, float nms,
+                     int relative, int letter, int max_rows) {
+    CUDA_OK(cudaSetDevice(e->opt.device));
+    ensure_slots(e);
+    const int k = e->next_slot;
+    Engine::Slot &sl = e->slots[k];
+    if (sl.busy) fatal_throw("submit: pipeline full (3 batches in flight) -- collect the oldest ticket first");
+    const DetParams P0 = det_params(e, net, sl.d_out, w, h, thresh, nms, relative, letter, max_rows);
+    const int B = e->batch, stride = 5 + P0.classes;
+    det_ws_ensure(sl.det, B, P0);
+    const size_t rows_bytes = (size_t)B * max_rows * stride * sizeof(float);
+    if (sl.h_rows_bytes < rows_bytes) {
+        if (sl.h_rows) cudaFreeHost(sl.h_rows);
+        CUDA_OK(cudaHostAlloc(&sl.h_rows, rows_bytes, cudaHostAllocDefault));
+        sl.h_rows_bytes = rows_bytes;
+    }
+    if (!sl.h_counts) CUDA_OK(cudaHostAlloc(&sl.h_counts, (size_t)B * sizeof(int), cudaHostAllocDefault));
+    const size_t bytes = (size_t)B * w * h * net->c;
+    if (bytes > sl.u8_bytes) {
+        if (sl.d_u8) cudaFree(sl.d_u8);
+        CUDA_OK(cudaMalloc(&sl.d_u8, bytes));
+        sl.u8_bytes = bytes;
+    }
+    e->next_slot = (k + 1) % (int)e->slots.size();
+    // the previous forward that read d_in[k] must have finished before it is overwritten
+    CUDA_OK(cudaStreamWaitEvent(e->s_in, sl.ev_comp, 0));
+    CUDA_OK(cudaMemcpyAsync(sl.d_u8, host_u8, bytes, cudaMemcpyHostToDevice, e->s_in));
+    const long total = (long)B * net->c * net->h * net->w;
+    k_resize_u8_to_nchw<<<grid_for(total), 256, 0, e->s_in>>>(sl.d_u8, B, w, h, net->c, sl.d_in, net->w, net->h);
+    CUDA_OK(cudaEventRecord(sl.ev_in, e->s_in));
+    CUDA_OK(cudaStreamWaitEvent(e->stream, sl.ev_in, 0));
+    engine_forward(e, sl.d_in, e->stream);
+    // earlier readers of d_out[k] (decode / D2H of the ticket that used this slot before) must be done
+    CUDA_OK(cudaStreamWaitEvent(e->stream, sl.ev_det, 0));
+    CUDA_OK(cudaStreamWaitEvent(e->stream, sl.ev_done, 0));
+    for (size_t i = 0; i < e->d_final.size(); ++i)
+        if (e->d_final[i] && (net->layers[i].type == YB_YOLO || net->layers[i].type == YB_REGION))
+            CUDA_OK(cudaMemcpyAsync(sl.d_out[i], e->d_final[i], e->final_count[i] * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+    CUDA_OK(cudaEventRecord(sl.ev_comp, e->stream));
+    CUDA_OK(cudaStreamWaitEvent(e->s_det, sl.ev_comp, 0));
+    det_launch_count_emit(P0, sl.det, B, e->s_det);
+    CUDA_OK(cudaMemcpyAsync(sl.h_counts, sl.det.counts, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, e->s_det));
+    det_launch_nms(P0, sl.det, B, max_rows, e->s_det);   // no host round trip: grids sized for the cap, kernels read the counts
+    CUDA_OK(cudaEventRecord(sl.ev_det, e->s_det));
+    CUDA_OK(cudaGetLastError());
+    sl.busy = true; sl.mode = 1;
+    return k;
+}
+
+// rows: pinned [batch][max_rows][5 + classes] (valid until the slot is reused), counts[batch]; returns 5 + classes.
+int engine_collect_detections(Engine *e, int ticket, const float **rows, const int **counts, size_t *d2h_bytes) {
+    if (ticket < 0 || ticket >= (int)e->slots.size() || !e->slots[ticket].busy || e->slots[ticket].mode != 1)
+        fatal_throw("collect_detections: bad ticket");
+    CUDA_OK(cudaSetDevice(e->opt.device));
+    Engine::Slot &sl = e->slots[ticket];
+    CUDA_OK(cudaEventSynchronize(sl.ev_det));
+    const int B = e->batch, cap = sl.det.cap, stride = sl.det.stride;
+    size_t moved = (size_t)B * sizeof(int);
+    for (int b = 0; b < B; ++b) {
+        const int n = std::min(sl.h_counts[b], cap);
+        if (n > 0) {
+            CUDA_OK(cudaMemcpyAsync(sl.h_rows + (size_t)b * cap * stride, sl.det.rows + (size_t)b * cap * stride,
+                                    (size_t)n * stride * sizeof(float), cudaMemcpyDeviceToHost, e->s_out));
+            moved += (size_t)n * stride * sizeof(float);
+        }
+    }
+    CUDA_OK(cudaStreamSynchronize(e->s_out));
+    if (rows) *rows = sl.h_rows;
+    if (counts) *counts = sl.h_counts;
+    if (d2h_bytes) *d2h_bytes = moved;
+    sl.busy = false;
     return stride;
 }
 

@@ -39,6 +39,13 @@ void engine_forward(Engine *e, const void *d_input, void *stream);
 void engine_download_outputs(Engine *e, Network *net, void *stream);   // async D2H into pinned, then sync
 int engine_submit(Engine *e, const float *host_input);
 void engine_collect(Engine *e, Network *net, int ticket);
+void engine_collect_ptrs(Engine *e, int ticket, std::vector<const float *> &ptrs, std::vector<size_t> &counts);
+const char *engine_broadcast_arena(const std::vector<Engine *> &replicas);   // "nccl" | "peer-copy" | "single"
+int engine_device_count();
+// pipelined u8 frames -> detections (device-side resize, forward, decode + NMS; only candidate rows come back)
+int engine_submit_u8(Engine *e, Network *net, const unsigned char *host_u8, int w, int h, float thresh, float nms,
+                     int relative, int letter, int max_rows);
+int engine_collect_detections(Engine *e, int ticket, const float **rows, const int **counts, size_t *d2h_bytes);
 void engine_fetch_layer(Engine *e, Network *net, int layer, float *dst);
 void engine_fetch_input(Engine *e, float *dst);
 int engine_fetch_counts(Engine *e, int layer, int32_t *dst, size_t count);

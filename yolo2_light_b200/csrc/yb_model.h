@@ -3,6 +3,7 @@
 #pragma once
 #include <cstdint>
 #include <cstdio>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -78,4 +79,13 @@ void abs_histogram_host(const float *src, size_t n, float bin_width, int max_bin
 
 struct yb_network {
     yb::Network net;
+    // multi-GPU batch extension (yb_network_predict_batch): replica engines [rule][k], k >= 1 (replica 0 is net.engine[rule]),
+    // the device of every replica, and the gathered host outputs [layer] = nimg x layer.outputs floats
+    std::vector<std::shared_ptr<yb::Engine>> replicas[2];
+    std::vector<int> devices;
+    std::string replication;                       // how the weights reached the replicas: "nccl" | "peer-copy" | "single"
+    std::vector<std::vector<float>> batch_out;
+    int batch_nimg = 0;
+    // single-layer networks of yb_forward_convolutional_layer, keyed by 2 * layer + variant (engines are built once)
+    std::map<int, std::unique_ptr<yb_network>> single;
 };
