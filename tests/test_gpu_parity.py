@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 
 import ybtest_util as util
+from yolo2_light_b200 import cfgs
 
 pytestmark = pytest.mark.gpu
 
@@ -393,3 +394,31 @@ def test_maxpool_fused_with_quantise_or_binarise_is_bit_exact(name, q, workdir):
         assert np.array_equal(res[0][1][i], res[1][1][i]), (name, i)
     for a, b in zip(res[0][2], res[1][2]):
         assert np.array_equal(a, b)
+
+
+# ---- XNOR layers outside the bit GEMM's shape (stride != 1 or pad != 1): the reference's float-GEMM fallback ----------
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+def test_xnor_stride_pad_fallback_matches_reference(workdir):
+    """yolov2_forward_network.c:40-50 + :204: such layers binarise the input to +-1 floats, swap in +-mean weights and run the
+    ordinary im2col + gemm_nn.  The engine does the same (k_binarize_pm1 + exact-order float conv): bit-identical."""
+    import yolo2_light_b200 as yb
+    from oracle import ref
+    secs = [cfgs._net(32, 32), cfgs._conv(8, 3), cfgs._conv(16, 3, 2, xnor=1), cfgs._conv(16, 1, xnor=1),
+            cfgs._conv(16, 3, xnor=1),                      # an ordinary XNOR layer behind them
+            cfgs._conv(18, 1, bn=False, act="linear"), cfgs._yolo("0,1,2", cfgs.COCO_ANCHORS, 9, classes=1)]
+    cfg = cfgs.write_cfg(secs, os.path.join(workdir, "xnor_fb.cfg"))
+    wts = cfgs.write_weights(secs, os.path.join(workdir, "xnor_fb.weights"), seed=23)
+    B = 2
+    x = cfgs.synthetic_images(B, 3, 32, 32, seed=24)
+    net = yb.load_network(cfg, wts, batch=B)
+    net.set_option("fuse", 0)
+    net.predict(x)
+    rnet = ref.RefNet(cfg, wts, 1, 0, 7)
+    for b in range(B):
+        rnet.predict(x[b:b + 1])
+        for i in range(4):
+            got = net.fetch_layer(i)[b]
+            exp = rnet.output(i)[0]
+            assert util.bits_equal(got, exp), (b, i, float(np.abs(got - exp).max()))
+        for i, o in net.detection_outputs().items():
+            assert util.rel_l2(o[b], rnet.output(i)[0].reshape(o[b].shape)) <= 1e-3

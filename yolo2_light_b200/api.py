@@ -528,14 +528,18 @@ def network_from_layers(descs: List[LayerDesc], batch: int, h: int, w: int, c: i
 
 
 class PinnedBuffer:
-    """cudaHostAlloc'ed float buffer for the end-to-end path."""
+    """cudaHostAlloc'ed buffer (float32 by default, or uint8 frames) for the end-to-end path."""
 
-    def __init__(self, count: int):
+    def __init__(self, count: int, dtype=np.float32):
         self.count = count
-        self._p = lib().yb_alloc_pinned(count * 4)
+        dt = np.dtype(dtype)
+        self._p = lib().yb_alloc_pinned(count * dt.itemsize)
         if not self._p:
             raise YbError("cudaHostAlloc failed")
-        self.array = np.ctypeslib.as_array(C.cast(self._p, C.POINTER(C.c_float)), shape=(count,))
+        ct = C.c_float if dt == np.float32 else C.c_uint8
+        if dt not in (np.dtype(np.float32), np.dtype(np.uint8)):
+            raise YbError("PinnedBuffer: float32 or uint8")
+        self.array = np.ctypeslib.as_array(C.cast(self._p, C.POINTER(ct)), shape=(count,))
 
     def __del__(self):
         try:

@@ -43,6 +43,7 @@ constexpr int TC_BM = 128;
 constexpr int TC_EPI_WARPS = 8;              // two warps per TMEM lane quarter, each takes half of the columns
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_ACC = 2;   // TMEM accumulator stages
+constexpr int TC_MAX_ASTAGES = 4;   // halo mode: A-ring depth (barriers are always reserved)
 
 struct TcParams {
     int N;                    // images
@@ -72,6 +73,18 @@ struct TcParams {
     int bstat;                                // 1: the whole filter matrix (nt == 1, <= 72 KB) is loaded once per CTA and stays in
                                               //    shared memory; the ring then streams activations only
     uint32_t bstat_bytes;
+    // Halo mode (3x3 / stride 1 / pad 1): the activation tile is loaded ONCE per channel block with its 1-pixel halo -- a
+    // [TH+2][TW+2] x BK box, TW = 8 -- and the nine taps are the same shared-memory tile read from line ky*(TW+2)+kx on, with
+    // the 8-row groups (TW+2) lines apart (descriptor SBO).  tcgen05 applies the swizzle to absolute address bits, so any start
+    // line and any SBO work (tools/probes/desc_probe.cu, profiles/r02_desc_probe.txt).  TMA bytes of A per K-block: 1/6.4 of
+    // the one-box-per-tap scheme.  A ring: a_stages x a_stage_bytes; the B ring keeps `stages` x b_bytes.
+    int halo, a_stages;
+    uint32_t a_stage_bytes, halo_bytes, halo_pitch;   // halo_pitch = (TW+2) * row bytes
+    uint32_t desc_hi_a;                       // descriptor high word of the halo A operand (SBO = halo_pitch)
+    // TMA epilogue (bf16 output, stride 1, BN >= 128): each group of four epilogue warps writes its 128 x 64-column slab as
+    // bf16 into a 128B-swizzled shared-memory tile and one thread stores it with cp.async.bulk.tensor; the shortcut residual
+    // comes in the same way (TMA load + mbarrier).  No shuffles, no staging transposes, no LSU global traffic, ~100 registers.
+    int tma_epi;
     int sps;                                  // K-blocks per pipeline stage (amortises the per-stage barrier round trip)
     int kbs;                                  // pipeline stages per work item = ceil(kblocks / sps)
     // K-split tail (wave quantisation): the last num_work % G work items ("tail") are cut along K into slices of sk_L
@@ -144,6 +157,17 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *tm,
     asm volatile(
         "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
         ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *tm, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -295,17 +319,22 @@ __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
 // contain no clock64() reads -- the single-thread producer / MMA roles are issue-bound on the BN <= 128 layers.
 template <int CG, bool KS, bool ST>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+          const __grid_constant__ CUtensorMap tmR, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smemB = (smem_u32(smem_raw) + 1023u) & ~1023u;   // 128B swizzle atoms are 1024B aligned
-    const uint32_t smem0 = smemB + p.bstat_bytes;                   // [resident filter matrix][pipeline ring]
+    const uint32_t smemA = smemB + p.bstat_bytes;                   // [resident filter matrix][halo A ring][pipeline ring]
+    const uint32_t smem0 = smemA + (uint32_t)p.a_stages * p.a_stage_bytes;
     const uint32_t bars = smem0 + (uint32_t)p.stages * p.stage_bytes;
     auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
     auto empty_bar = [&](int s) { return bars + 8u * (uint32_t)(p.stages + s); };
     auto tfull_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * p.stages + a); };
     auto tempty_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * p.stages + TC_ACC + a); };
     const uint32_t bstat_bar = bars + 8u * (uint32_t)(2 * p.stages + 2 * TC_ACC);
-    const uint32_t tmem_slot = bstat_bar + 8u;
+    auto fullA_bar = [&](int s) { return bstat_bar + 8u + 8u * (uint32_t)s; };          // halo mode: the A ring's own barriers
+    auto emptyA_bar = [&](int s) { return bstat_bar + 8u + 8u * (uint32_t)(TC_MAX_ASTAGES + s); };
+    auto resfull_bar = [&](int g) { return bstat_bar + 8u + 8u * (uint32_t)(2 * TC_MAX_ASTAGES + g); };   // TMA epilogue: residual landed
+    const uint32_t tmem_slot = bstat_bar + 8u + 8u * (uint32_t)(2 * TC_MAX_ASTAGES + 2);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
@@ -323,6 +352,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < TC_ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), CG * TC_EPI_WARPS); }
         mbar_init(bstat_bar, 1);
+        for (int s = 0; s < TC_MAX_ASTAGES; ++s) { mbar_init(fullA_bar(s), 1); mbar_init(emptyA_bar(s), 1); }
+        mbar_init(resfull_bar(0), 1); mbar_init(resfull_bar(1), 1);
+        if (p.tma_epi) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
+            if (p.res) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -339,7 +374,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // 4 KB of staging per epilogue warp (32 rows x 128 B, XOR-swizzled) for the coalescing transposes
     // fused [yolo]: one bit per filter, set where the entry is a box width/height (no logistic)
     uint32_t *ymask_s = reinterpret_cast<uint32_t *>(bias_s + p.nt * p.BN);
-    const uint32_t stg_base = ((tmem_slot + 16u + 4u * (uint32_t)(p.nt * p.BN) + (uint32_t)(p.nt * p.BN / 8)) + 127u) & ~127u;
+    const uint32_t stg_align = p.tma_epi ? 1023u : 127u;     // TMA epilogue tiles are 128B-swizzled: 1024-byte aligned
+    const uint32_t stg_base = ((tmem_slot + 16u + 4u * (uint32_t)(p.nt * p.BN) + (uint32_t)(p.nt * p.BN / 8)) + stg_align) & ~stg_align;
     for (int i = threadIdx.x; i < p.nt * p.BN; i += TC_THREADS) bias_s[i] = (i < p.n) ? __ldg(p.bias + i) : 0.f;
     if (p.yolo_out) {
         for (int wd = threadIdx.x; wd < p.nt * p.BN / 32; wd += TC_THREADS) {
@@ -375,6 +411,50 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 mbar_arrive_expect_tx(bstat_bar, p.bstat_bytes);
                 for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(smemB + (uint32_t)kb * b_bytes, &tmB, bstat_bar, kb * BK, 0);
             }
+            if (p.halo) {
+                // ---- halo mode: unit = (work item, channel block); the A tile of unit u+1 is requested before the nine filter
+                // tiles of unit u, so the activation ring runs one unit ahead of the MMAs
+                const int SA = p.a_stages;
+                const uint32_t a_stage_bytes = p.a_stage_bytes, halo_bytes = p.halo_bytes;
+                int sa = 0; uint32_t pha = 0;
+                TcSched schA = sched_init<false>(p, w_first, w_step);
+                int wA = 0, cbA = cblocks, d0, d1;
+                auto next_A = [&]() {
+                    if (cbA == cblocks) { if (!sched_next<false>(schA, wA, d0, d1)) return; cbA = 0; }
+                    const int m = (CG == 2) ? 2 * (wA / nt) + (int)rank : wA / nt;
+                    const int x0 = (m % xt) * p.TW, J0 = (m / xt) * p.TH;
+                    if constexpr (ST) { const long long c0 = clock64(); mbar_wait(emptyA_bar(sa), pha ^ 1u, 5); w_tma += clock64() - c0; }   // [7]: wait on the A ring
+                    else mbar_wait(emptyA_bar(sa), pha ^ 1u, 5);
+                    const uint32_t fb = fullA_bar(sa);
+                    if (leader) mbar_arrive_expect_tx(fb, (uint32_t)CG * halo_bytes);
+                    const uint32_t ad = smemA + (uint32_t)sa * a_stage_bytes;
+                    if constexpr (CG == 2) tma2_load_3d(ad, &tmA, fb, cbA * BK, x0, J0 - 1);
+                    else tma_load_3d(ad, &tmA, fb, cbA * BK, x0, J0 - 1);
+                    ++cbA;
+                    if (++sa == SA) { sa = 0; pha ^= 1u; }
+                };
+                next_A();
+                TcSched sch = sched_init<false>(p, w_first, w_step);
+                int w, seg0, seg1;
+                while (sched_next<false>(sch, w, seg0, seg1)) {
+                    const int n0 = (w % nt) * p.BN + (int)rank * (p.BN / CG);
+                    for (int cb = 0; cb < cblocks; ++cb) {
+                        next_A();
+                        if (bstat) continue;
+                        int kcol = cb * BK;                      // K is ordered (tap, channel): tap t of this block at t*C + cb*BK
+                        for (int t = 0; t < 9; ++t, kcol += cblocks * BK) {
+                            if constexpr (ST) { const long long c0 = clock64(); mbar_wait(empty_bar(stage), phase ^ 1u, 0); w_empty += clock64() - c0; }
+                            else mbar_wait(empty_bar(stage), phase ^ 1u, 0);
+                            const uint32_t fb = full_bar(stage);
+                            if (leader) mbar_arrive_expect_tx(fb, (uint32_t)CG * b_bytes);
+                            const uint32_t bd = smem0 + (uint32_t)stage * stage_bytes;
+                            if constexpr (CG == 2) tma2_load_2d(bd, &tmB, fb, kcol, n0);
+                            else tma_load_2d(bd, &tmB, fb, kcol, n0);
+                            if (++stage == stages) { stage = 0; phase ^= 1u; }
+                        }
+                    }
+                }
+            } else {
             TcSched sch = sched_init<KS>(p, w_first, w_step);
             int w, seg0, seg1;
             while (sched_next<KS>(sch, w, seg0, seg1)) {
@@ -421,71 +501,174 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     if (++stage == stages) { stage = 0; phase ^= 1u; }
                 }
             }
+            }
             if (ST && p.stats) { p.stats[blockIdx.x * 8 + 0] = (unsigned long long)w_empty; p.stats[blockIdx.x * 8 + 1] = (unsigned long long)(clock64() - t_begin); p.stats[blockIdx.x * 8 + 7] = (unsigned long long)w_tma; }
         }
     } else if (warp == 1) {
         // ======================= MMA issuer (CG=2: the leader CTA only, for both CTAs) =======================
-        // the operand kind is fixed per launch: one copy of the issue loop per kind, chosen once -- a per-MMA branch on it
-        // costs the single issuing thread ~2 % of the whole yolov3 step (the BN <= 128 layers are issue-bound)
-        auto mma_role = [&](auto kind_c) {
+        // One thread issues every tcgen05.mma.  Measured (tools/probes/issue_probe.cu, profiles/r02_issue_probe.txt): an MMA
+        // costs the issuing thread ~53 cycles, a loop trip ~230 more, commits are free -- so MMAs are issued in straight-line
+        // batches of 8-18 (two pipeline stages, three taps, or a whole channel block at once), descriptors first.  The operand
+        // kind and the MMAs per K-block are compile-time: one copy of the role per (kind, kk), chosen once per launch.
+        auto mma_role = [&](auto kind_c, auto kk_c) {
             constexpr int KIND = decltype(kind_c)::value;
+            constexpr int KK = decltype(kk_c)::value;
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            const int kk = p.kk, sps = p.sps, kblocks = p.kblocks, stages = p.stages, BN = p.BN;
-            const uint32_t a_bytes = p.a_bytes, b_bytes = p.b_bytes, stage_bytes = p.stage_bytes, idesc = p.idesc, dbg = (uint32_t)p.dbg;
+            const int sps = p.sps, kblocks = p.kblocks, stages = p.stages, BN = p.BN;
+            const uint32_t a_bytes = p.a_bytes, b_bytes = p.b_bytes, stage_bytes = p.stage_bytes, idesc = p.idesc;
             const uint32_t b_off = (uint32_t)sps * a_bytes;
-            const uint64_t hi = (uint64_t)p.desc_hi << 32;
+            const uint32_t bhi = p.desc_hi;
             long long w_full = 0, w_tempty = 0; const long long t_begin = ST ? clock64() : 0;
             const int bstat = p.bstat;
             if (bstat) { mbar_wait(bstat_bar, 0, 4); tc_fence_after(); }
-            TcSched sch = sched_init<KS>(p, w_first, w_step);
-            int w, seg0, seg1;
-            while (sched_next<KS>(sch, w, seg0, seg1)) {
-                // epilogue(s) drained this accumulator
+            auto lo = [](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); };   // descriptor low word: address, LBO = 1
+            // the KK MMAs of one K-block: K advance of 16 bf16 / 32 s8 / 8 tf32 = 32 bytes inside the swizzle row = +2 units
+            auto issue_kb = [&](uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t first) {
+#pragma unroll
+                for (int k = 0; k < KK; ++k) {
+                    const uint64_t adesc = ((uint64_t)ahi << 32) | (uint64_t)(alo + 2u * (uint32_t)k);
+                    const uint64_t bdesc = ((uint64_t)bhi << 32) | (uint64_t)(blo + 2u * (uint32_t)k);
+                    const uint32_t accum = (k == 0) ? (uint32_t)(first != 0u) : 1u;
+                    if constexpr (CG == 2) umma2_bf16(d_tmem, adesc, bdesc, idesc, accum);
+                    else if constexpr (KIND == 3) umma_tf32(d_tmem, adesc, bdesc, idesc, accum);
+                    else if constexpr (KIND == 1) umma_i8(d_tmem, adesc, bdesc, idesc, accum);
+                    else umma_bf16(d_tmem, adesc, bdesc, idesc, accum);
+                }
+            };
+            auto wait_tempty = [&]() {   // the epilogue(s) drained this accumulator
                 if constexpr (ST) { const long long c0 = clock64(); mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 1); w_tempty += clock64() - c0; }
                 else mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                const int kb_begin = seg0 * sps, kb_end = min(kblocks, seg1 * sps);
-                for (int kb0 = kb_begin; kb0 < kb_end; kb0 += sps) {
-                    const int nsub = min(sps, kb_end - kb0);
-                    // TMA bytes have landed
-                    if constexpr (ST) { const long long c0 = clock64(); mbar_wait(full_bar(stage), phase, 2); w_full += clock64() - c0; }
-                    else mbar_wait(full_bar(stage), phase, 2);
-                    tc_fence_after();
-                    const uint32_t a_base = smem0 + (uint32_t)stage * stage_bytes;
-                    const uint32_t b_base = a_base + b_off;
-                    for (int j = 0; j < nsub && !(dbg & 2); ++j) {
-                        // K-major operands; K advance of 16 bf16 = 32 bytes inside the swizzle row = +2 in the
-                        // descriptor's 16-byte address units
-                        uint64_t adesc = hi | (uint64_t)((((a_base + (uint32_t)j * a_bytes) & 0x3FFFFu) >> 4) | (1u << 16));
-                        const uint32_t b_src = bstat ? smemB + (uint32_t)(kb0 + j) * b_bytes : b_base + (uint32_t)j * b_bytes;
-                        uint64_t bdesc = hi | (uint64_t)(((b_src & 0x3FFFFu) >> 4) | (1u << 16));
-                        const int first = (kb0 - kb_begin) | j;     // 0 on the first K-block of the segment: overwrite the accumulator
-                        for (int k = 0; k < kk; ++k) {
-                            if constexpr (CG == 2) umma2_bf16(d_tmem, adesc, bdesc, idesc, (uint32_t)((first | k) != 0));
-                            else if constexpr (KIND == 3) umma_tf32(d_tmem, adesc, bdesc, idesc, (uint32_t)((first | k) != 0));
-                            else if constexpr (KIND == 1) umma_i8(d_tmem, adesc, bdesc, idesc, (uint32_t)((first | k) != 0));
-                            else umma_bf16(d_tmem, adesc, bdesc, idesc, (uint32_t)((first | k) != 0));
-                            adesc += 2; bdesc += 2;
+            };
+            auto wait_full = [&](int st_, uint32_t ph_) {   // TMA bytes of a ring stage have landed
+                if constexpr (ST) { const long long c0 = clock64(); mbar_wait(full_bar(st_), ph_, 2); w_full += clock64() - c0; }
+                else mbar_wait(full_bar(st_), ph_, 2);
+            };
+            auto release = [&](uint32_t bar) {   // arrives on `bar` (of both CTAs) when every MMA issued so far has retired
+                if constexpr (CG == 2) umma2_commit_both(bar); else umma_commit(bar);
+            };
+            if (p.halo) {
+                // ---- halo mode: per channel block one activation tile (with halo) and nine filter tiles; tap (ky, kx) reads the
+                // activation tile from line ky*(TW+2) + kx on
+                const int SA = p.a_stages, cblocks = p.cblocks;
+                const uint32_t a_stage_bytes = p.a_stage_bytes, pitch = p.halo_pitch, rb = pitch / (uint32_t)(p.TW + 2);
+                const uint32_t ahi = p.desc_hi_a;
+                int sa = 0; uint32_t pha = 0;
+                TcSched sch = sched_init<false>(p, w_first, w_step);
+                int w, seg0, seg1;
+                while (sched_next<false>(sch, w, seg0, seg1)) {
+                    wait_tempty();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                    for (int cb = 0; cb < cblocks; ++cb) {
+                        if constexpr (ST) { const long long c0 = clock64(); mbar_wait(fullA_bar(sa), pha, 6); w_full += clock64() - c0; }
+                        else mbar_wait(fullA_bar(sa), pha, 6);
+                        tc_fence_after();
+                        const uint32_t a_tile = smemA + (uint32_t)sa * a_stage_bytes;
+                        if (bstat) {
+                            // resident filter matrix: all nine taps of the channel block in one straight-line batch
+                            const uint32_t b0 = smemB + (uint32_t)cb * b_bytes, bstep = (uint32_t)cblocks * b_bytes;
+#pragma unroll
+                            for (int t = 0; t < 9; ++t)
+                                issue_kb(d_tmem, lo(a_tile + (uint32_t)(t / 3) * pitch + (uint32_t)(t % 3) * rb), ahi,
+                                         lo(b0 + (uint32_t)t * bstep), (uint32_t)(cb | t));
+                        } else {
+                            for (int ky = 0; ky < 3; ++ky) {        // one filter row = three K-blocks per batch
+                                uint32_t blo[3], ebar[3];
+#pragma unroll
+                                for (int kx = 0; kx < 3; ++kx) {
+                                    wait_full(stage, phase);
+                                    blo[kx] = lo(smem0 + (uint32_t)stage * stage_bytes);
+                                    ebar[kx] = empty_bar(stage);
+                                    if (++stage == stages) { stage = 0; phase ^= 1u; }
+                                }
+                                tc_fence_after();
+                                const uint32_t a_row = a_tile + (uint32_t)ky * pitch;
+                                // each stage's commit right behind its own MMAs (a commit covers everything issued before it: issued at
+                                // the end of the batch, all three stages would come free together and a ring shallower than 2 batches
+                                // + 1 would stall once per batch -- measured: +40 % on the deep-K layers with 5 stages)
+#pragma unroll
+                                for (int kx = 0; kx < 3; ++kx) {
+                                    issue_kb(d_tmem, lo(a_row + (uint32_t)kx * rb), ahi, blo[kx], (uint32_t)(cb | ky | kx));
+                                    release(ebar[kx]);
+                                }
+                            }
+                        }
+                        release(emptyA_bar(sa));
+                        if (++sa == SA) { sa = 0; pha ^= 1u; }
+                    }
+                    release(tfull_bar(acc));     // accumulator complete -> epilogue warps (of both CTAs)
+                    if (++acc == TC_ACC) { acc = 0; acc_phase ^= 1u; }
+                }
+            } else {
+                const uint32_t ahi = p.desc_hi;
+                TcSched sch = sched_init<KS>(p, w_first, w_step);
+                int w, seg0, seg1;
+                while (sched_next<KS>(sch, w, seg0, seg1)) {
+                    wait_tempty();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                    const int kb_begin = seg0 * sps, kb_end = min(kblocks, seg1 * sps);
+                    int kb0 = kb_begin;
+                    while (kb0 < kb_end) {
+                        // one batch = the K-blocks of one stage (sps > 1) or of two consecutive stages (sps == 1): up to 4 entries
+                        uint32_t alo[4], blo[4], ebar[2];
+                        int ne = 0, nst = 1;
+                        {   // first (or only) stage of the batch: entries 0 .. nsub-1
+                            const int nsub = min(sps, kb_end - kb0);
+                            wait_full(stage, phase);
+                            const uint32_t a_base = smem0 + (uint32_t)stage * stage_bytes, b_base = a_base + b_off;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                alo[j] = lo(a_base + (uint32_t)j * a_bytes);
+                                blo[j] = lo(bstat ? smemB + (uint32_t)(kb0 + j) * b_bytes : b_base + (uint32_t)j * b_bytes);
+                            }
+                            ne = nsub;
+                            ebar[0] = empty_bar(stage);
+                            kb0 += nsub;
+                            if (++stage == stages) { stage = 0; phase ^= 1u; }
+                        }
+                        if (sps == 1 && kb0 < kb_end) {   // one K-block per stage: take the next stage into the same batch (entry 1)
+                            wait_full(stage, phase);
+                            const uint32_t a_base = smem0 + (uint32_t)stage * stage_bytes;
+                            alo[1] = lo(a_base);
+                            blo[1] = lo(bstat ? smemB + (uint32_t)kb0 * b_bytes : a_base + b_off);
+                            ne = 2; nst = 2;
+                            ebar[1] = empty_bar(stage);
+                            kb0 += 1;
+                            if (++stage == stages) { stage = 0; phase ^= 1u; }
+                        } else ebar[1] = 0u;
+                        tc_fence_after();
+                        const uint32_t first = (uint32_t)(kb0 - kb_begin - ne);   // 0 on the first K-block of the segment: overwrite
+                        // frees the smem stages (in both CTAs) when their MMAs retire: each stage's commit right behind its own MMAs
+                        if (nst == 2) {
+                            issue_kb(d_tmem, alo[0], ahi, blo[0], first);
+                            release(ebar[0]);
+                            issue_kb(d_tmem, alo[1], ahi, blo[1], 1u);
+                            release(ebar[1]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (e < ne) issue_kb(d_tmem, alo[e], ahi, blo[e], first | (uint32_t)e);
+                            release(ebar[0]);
                         }
                     }
-                    // frees the smem stage (in both CTAs) when these MMAs retire
-                    if constexpr (CG == 2) umma2_commit_both(empty_bar(stage)); else umma_commit(empty_bar(stage));
-                    if (++stage == stages) { stage = 0; phase ^= 1u; }
+                    release(tfull_bar(acc));     // accumulator complete -> epilogue warps (of both CTAs)
+                    if (++acc == TC_ACC) { acc = 0; acc_phase ^= 1u; }
                 }
-                // accumulator complete -> epilogue warps (of both CTAs)
-                if constexpr (CG == 2) umma2_commit_both(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
-                if (++acc == TC_ACC) { acc = 0; acc_phase ^= 1u; }
             }
             if (ST && p.stats) { p.stats[blockIdx.x * 8 + 2] = (unsigned long long)w_full; p.stats[blockIdx.x * 8 + 3] = (unsigned long long)w_tempty;
-                           p.stats[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_begin); }
+                                 p.stats[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_begin); }
         };
         if (leader && elect_one()) {
-            if constexpr (CG == 2) mma_role(std::integral_constant<int, 0>{});
-            else if (p.kind == 0) mma_role(std::integral_constant<int, 0>{});
-            else if (p.kind == 3) mma_role(std::integral_constant<int, 3>{});
-            else mma_role(std::integral_constant<int, 1>{});
+            auto by_kk = [&](auto kind_c) {
+                if (p.kk == 4) mma_role(kind_c, std::integral_constant<int, 4>{});
+                else if (p.kk == 2) mma_role(kind_c, std::integral_constant<int, 2>{});
+                else mma_role(kind_c, std::integral_constant<int, 1>{});
+            };
+            if constexpr (CG == 2) by_kk(std::integral_constant<int, 0>{});
+            else if (p.kind == 0) by_kk(std::integral_constant<int, 0>{});
+            else if (p.kind == 3) by_kk(std::integral_constant<int, 3>{});
+            else by_kk(std::integral_constant<int, 1>{});
         }
     } else {
         // ======================= epilogue (warps 2..9) =======================
@@ -500,6 +683,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int tx = r & (p.TW - 1), ty = r >> p.TWlog2;
         const bool leaky = p.act == ACT_LEAKY, leaky2 = p.act2 == ACT_LEAKY;
         int acc = 0; uint32_t acc_phase = 0;
+        uint32_t epi_res_phase = 0;               // TMA epilogue: parity of this group's residual barrier
         long long w_tfull = 0; const long long t_begin = ST ? clock64() : 0;
         TcSched sch = sched_init<KS>(p, w_first, w_step);
         int w, seg0, seg1;
@@ -533,15 +717,39 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             };
             // the staged bf16 store paths fetch their own residual, the integer / tf32 kinds never have one: rv[] is only
             // prefetched for the per-thread store path (f32 heads, YB_TC_NO_COALESCE)
-            const bool own_res = (p.out_bf16 && ((cend - cbeg) >= 64 || (cend - cbeg) == 32) && !p.no_coalesce) || p.kind != 0 || !p.res;
+            const bool own_res = (p.out_bf16 && ((cend - cbeg) >= 64 || (cend - cbeg) == 32) && !p.no_coalesce) || p.kind != 0 || !p.res || p.tma_epi;
             if (!own_res) {
                 if (cbeg < cend) load_res(cbeg, rv[0]);
                 if (cend - cbeg > 32) load_res(cbeg + 32, rv[1]);
             }
 
-            if constexpr (ST) { const long long c0 = clock64(); mbar_wait(tfull_bar(acc), acc_phase, 3); w_tfull += clock64() - c0; }
-            else mbar_wait(tfull_bar(acc), acc_phase, 3);
-            tc_fence_after();
+            // The 64-column staged store path is decided here, before the accumulator wait, so that its first residual fetch
+            // overlaps the wait.  Residual (fused shortcut): 8 independent 16-byte loads per thread go out TOGETHER into
+            // registers (rres) and only later into the staging tile.  (Round 1 stored every value right behind its load inside
+            // one asm-volatile sequence: eight fully serialised global-load latencies per 64-column slab, ~5 k cycles -- that,
+            // not the tensor pipe or TMA, bounded every shortcut-fused 3x3 layer; profiles/r02_notes.md.)
+            const bool path64 = !seg_partial && !p.tma_epi && p.kind != 1 && p.kind != 2 && p.out_bf16 && (cend - cbeg) >= 64 && !p.no_coalesce;
+            const int srow = lane >> 3, schunk = lane & 7;
+            const unsigned long long rbase = (unsigned long long)(uintptr_t)rrow;
+            uint4 rres[8];
+            auto res_load = [&](int f0) {          // coalesced global -> registers (whole 128-byte lines per 8 lanes)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const unsigned long long rp = __shfl_sync(0xffffffffu, rbase, i * 4 + srow);
+                    rres[i] = make_uint4(0u, 0u, 0u, 0u);
+                    if (rp && (n0 + f0 + schunk * 8) < p.n_store)
+                        rres[i] = __ldg(reinterpret_cast<const uint4 *>(rp + (size_t)(n0 + f0) * 2) + schunk);
+                }
+            };
+            if (path64 && p.res) res_load(cbeg);
+
+            // (the TMA epilogue requests its first residual tile before this wait and waits itself)
+            const bool tfull_waited = !p.tma_epi;
+            if (tfull_waited) {
+                if constexpr (ST) { const long long c0 = clock64(); mbar_wait(tfull_bar(acc), acc_phase, 3); w_tfull += clock64() - c0; }
+                else mbar_wait(tfull_bar(acc), acc_phase, 3);
+                tc_fence_after();
+            }
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
 
             if constexpr (KS) {
@@ -680,31 +888,149 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 }
             };
 
+            // ---- coalesced f32 store of one 32-column slab (the integer kinds and the f32 heads): a row is 128 B; the warp's 32
+            // rows go through its private XOR-swizzled 4 KB staging tile so that every global store instruction writes 4 rows x
+            // 128 contiguous bytes instead of 32 rows x 16 B (32 different lines per instruction: what kept the early INT8
+            // layers at 0.8 TB/s in round 1)
+            auto store_f32_slab = [&](const float (&y)[32], int f0) {
+                const uint32_t stg = stg_base + (uint32_t)(warp - 2) * 4096u;
+                const int srow = lane >> 3, schunk = lane & 7;
+                const unsigned long long obase = (unsigned long long)(uintptr_t)orow;
+                const int vflag = valid ? 1 : 0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)lane * 128u + (uint32_t)((c ^ (lane & 7)) << 4)),
+                                 "r"(__float_as_uint(y[c * 4 + 0])), "r"(__float_as_uint(y[c * 4 + 1])),
+                                 "r"(__float_as_uint(y[c * 4 + 2])), "r"(__float_as_uint(y[c * 4 + 3])) : "memory");
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = i * 4 + srow;
+                    const unsigned long long op = __shfl_sync(0xffffffffu, obase, row);
+                    const int ok = __shfl_sync(0xffffffffu, vflag, row);
+                    uint32_t w0, w1, w2, w3;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                                 : "r"(stg + (uint32_t)row * 128u + (uint32_t)((schunk ^ (row & 7)) << 4)) : "memory");
+                    if (ok && (n0 + f0 + schunk * 4) < p.n_store)
+                        *(reinterpret_cast<uint4 *>(op + (size_t)(n0 + f0) * 4) + schunk) = make_uint4(w0, w1, w2, w3);
+                }
+                __syncwarp();
+            };
+
+            if (p.tma_epi) {
+                // ---- TMA epilogue.  Group g = the four warps that own column half `half` (128 threads, named barrier 1 + half);
+                // per slab of SW = 64 (or 32) columns: [OUT tile][RES tile], both [128 pixel rows][SW * 2 bytes] with the swizzle of
+                // the tensor maps -- 16-byte chunk c of row r at r*128 + ((c ^ (r & 7)) << 4) for 128-byte rows, at r*64 +
+                // ((c ^ ((r >> 1) & 3)) << 4) for 64-byte rows: conflict-free for one thread per row.
+                auto slabs = [&](auto nv_c) {
+                    constexpr int NV = decltype(nv_c)::value;          // tcgen05.ld.x32 per slab: 2 (SW = 64) or 1 (SW = 32)
+                    constexpr int SW = 32 * NV;
+                    constexpr uint32_t tile_bytes = 128u * SW * 2u, rowb = SW * 2u;
+                    const int g = half;
+                    const uint32_t out_tile = stg_base + (uint32_t)g * (2u * tile_bytes), res_tile = out_tile + tile_bytes;
+                    const bool boss = (q == 0) && (lane == 0);           // issues this group's TMA traffic
+                    const int x0 = (m % p.xt) * p.TW, J0 = (m / p.xt) * p.TH;
+                    const uint32_t rsw = (NV == 2) ? (uint32_t)(r & 7) : (uint32_t)((r >> 1) & 3);
+                    const uint32_t row_off = (uint32_t)r * rowb;
+                    const bool has_res = p.res != nullptr;
+                    if (has_res && boss) {                                // first slab's residual: flies under the accumulator wait
+                        mbar_arrive_expect_tx(resfull_bar(g), tile_bytes);
+                        tma_load_3d(res_tile, &tmR, resfull_bar(g), n0 + cbeg, x0 + 1, J0);
+                    }
+                    if (!tfull_waited) {
+                        if constexpr (ST) { const long long c0 = clock64(); mbar_wait(tfull_bar(acc), acc_phase, 3); w_tfull += clock64() - c0; }
+                        else mbar_wait(tfull_bar(acc), acc_phase, 3);
+                        tc_fence_after();
+                    }
+                    for (int f0 = cbeg; f0 < cend; f0 += SW) {
+                        uint32_t v[NV][32];
+#pragma unroll
+                        for (int h2 = 0; h2 < NV; ++h2) tmem_ld32(taddr + (uint32_t)(f0 + 32 * h2), v[h2]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int h2 = 0; h2 < NV; ++h2)
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float a0 = __uint_as_float(v[h2][j]) + bs[f0 + 32 * h2 + j];
+                                v[h2][j] = __float_as_uint(leaky ? fmaxf(a0, 0.1f * a0) : a0);
+                            }
+                        if (has_res) {
+                            mbar_wait(resfull_bar(g), epi_res_phase, 7);
+                            epi_res_phase ^= 1u;
+#pragma unroll
+                            for (int c = 0; c < 4 * NV; ++c) {             // own row of the residual tile, 16 bytes at a time
+                                uint32_t w0, w1, w2, w3;
+                                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                                             : "r"(res_tile + row_off + (((uint32_t)c ^ rsw) << 4)) : "memory");
+                                const uint32_t wv[4] = {w0, w1, w2, w3};
+#pragma unroll
+                                for (int h = 0; h < 4; ++h) {
+                                    uint32_t &lo_ = v[c / 4][(c % 4) * 8 + 2 * h], &hi_ = v[c / 4][(c % 4) * 8 + 2 * h + 1];
+                                    float a = __uint_as_float(lo_) + __uint_as_float(wv[h] << 16);
+                                    float b = __uint_as_float(hi_) + __uint_as_float(wv[h] & 0xffff0000u);
+                                    if (leaky2) { a = fmaxf(a, 0.1f * a); b = fmaxf(b, 0.1f * b); }
+                                    lo_ = __float_as_uint(a); hi_ = __float_as_uint(b);
+                                }
+                            }
+                        }
+                        // the previous slab's TMA store must have finished READING the OUT tile before it is overwritten
+                        if (boss) tma_store_wait_read0();
+                        named_bar_sync(1 + g, 128);
+                        if (has_res && boss && f0 + SW < cend) {           // everybody is done with the RES tile: request the next one
+                            mbar_arrive_expect_tx(resfull_bar(g), tile_bytes);
+                            tma_load_3d(res_tile, &tmR, resfull_bar(g), n0 + f0 + SW, x0 + 1, J0);
+                        }
+#pragma unroll
+                        for (int c = 0; c < 4 * NV; ++c) {                 // own row -> OUT tile (border / padding rows: zeros)
+                            const uint32_t *src = &v[c / 4][(c % 4) * 8];
+                            uint32_t o0 = pack_bf16x2(__uint_as_float(src[0]), __uint_as_float(src[1]));
+                            uint32_t o1 = pack_bf16x2(__uint_as_float(src[2]), __uint_as_float(src[3]));
+                            uint32_t o2 = pack_bf16x2(__uint_as_float(src[4]), __uint_as_float(src[5]));
+                            uint32_t o3 = pack_bf16x2(__uint_as_float(src[6]), __uint_as_float(src[7]));
+                            if (!valid) { o0 = o1 = o2 = o3 = 0u; }
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(out_tile + row_off + (((uint32_t)c ^ rsw) << 4)),
+                                         "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA engine
+                        named_bar_sync(1 + g, 128);
+                        if (boss) {
+                            tma_store_3d(&tmO, out_tile, n0 + f0, x0 + 1, J0);
+                            tma_store_commit();
+                        }
+                    }
+                };
+                if (p.tma_epi == 64) slabs(std::integral_constant<int, 2>{});
+                else slabs(std::integral_constant<int, 1>{});
+            } else
             if (seg_partial) {
                 // accumulator already published above
             } else
             if (p.kind == 2) {
                 // ---- XNOR as +-1 int8: acc == 2*count - K (exact); out = act((float)acc * mean + bias) in the reference's
                 // float op order (additionally.c:1531, yolov2_forward_network.c:243-261)
-                float *orow_f = reinterpret_cast<float *>(orow);
                 for (int f0 = cbeg; f0 < cend; f0 += 32) {
                     uint32_t v0[32];
                     tmem_ld32(taddr + (uint32_t)f0, v0);
                     tmem_ld_wait();
-                    if (!valid) continue;
+                    float y[32];
 #pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        if (n0 + f0 + g * 4 >= p.n_store) break;
-                        float y[4];
-#pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            const int f = n0 + f0 + g * 4 + h;
-                            float t = __fmul_rn((float)(int)v0[g * 4 + h], (f < p.n) ? __ldg(p.mean + f) : 0.f);
-                            t = __fadd_rn(t, bs[f0 + g * 4 + h]);
-                            y[h] = act_exact(t, p.act);
-                        }
-                        *reinterpret_cast<float4 *>(orow_f + n0 + f0 + g * 4) = make_float4(y[0], y[1], y[2], y[3]);
+                    for (int j = 0; j < 32; ++j) {
+                        const int f = n0 + f0 + j;
+                        float t = __fmul_rn((float)(int)v0[j], (f < p.n) ? __ldg(p.mean + f) : 0.f);
+                        t = __fadd_rn(t, bs[f0 + j]);
+                        y[j] = act_exact(t, p.act);
                     }
+                    if (p.no_coalesce) {
+                        if (valid) {
+                            float *orow_f = reinterpret_cast<float *>(orow);
+#pragma unroll
+                            for (int g = 0; g < 8; ++g) {
+                                if (n0 + f0 + g * 4 >= p.n_store) break;
+                                *reinterpret_cast<float4 *>(orow_f + n0 + f0 + g * 4) = make_float4(y[g * 4], y[g * 4 + 1], y[g * 4 + 2], y[g * 4 + 3]);
+                            }
+                        }
+                    } else store_f32_slab(y, f0);
+                    if (!valid) continue;
                     if (p.acc_out) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
@@ -717,27 +1043,31 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             if (p.kind == 1) {
                 // ---- INT8: exact requantisation of the reference (yolov2_forward_network_quantized.c:474-490, :598-627):
                 // q16 = clamp(+-32767, acc / 32) [C truncating division]; y = (float)q16 * ALPHA1; y += bias; leaky: y / 10.
-                float *orow_f = reinterpret_cast<float *>(orow);
                 for (int f0 = cbeg; f0 < cend; f0 += 32) {
                     uint32_t v0[32];
                     tmem_ld32(taddr + (uint32_t)f0, v0);
                     tmem_ld_wait();
-                    if (!valid) continue;
+                    float y[32];
 #pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        if (n0 + f0 + g * 4 >= p.n_store) break;
-                        float y[4];
-#pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            const int a = (int)v0[g * 4 + h];
-                            int q16 = a / 32;
-                            q16 = q16 > 32767 ? 32767 : (q16 < -32767 ? -32767 : q16);
-                            float t = __fmul_rn((float)q16, p.alpha1);
-                            t = __fadd_rn(t, bs[f0 + g * 4 + h]);
-                            y[h] = (p.act == ACT_LEAKY) ? ((t > 0.f) ? t : __fdiv_rn(t, 10.f)) : t;
-                        }
-                        *reinterpret_cast<float4 *>(orow_f + n0 + f0 + g * 4) = make_float4(y[0], y[1], y[2], y[3]);
+                    for (int j = 0; j < 32; ++j) {
+                        const int a = (int)v0[j];
+                        int q16 = a / 32;
+                        q16 = q16 > 32767 ? 32767 : (q16 < -32767 ? -32767 : q16);
+                        float t = __fmul_rn((float)q16, p.alpha1);
+                        t = __fadd_rn(t, bs[f0 + j]);
+                        y[j] = (p.act == ACT_LEAKY) ? ((t > 0.f) ? t : __fdiv_rn(t, 10.f)) : t;
                     }
+                    if (p.no_coalesce) {
+                        if (valid) {
+                            float *orow_f = reinterpret_cast<float *>(orow);
+#pragma unroll
+                            for (int g = 0; g < 8; ++g) {
+                                if (n0 + f0 + g * 4 >= p.n_store) break;
+                                *reinterpret_cast<float4 *>(orow_f + n0 + f0 + g * 4) = make_float4(y[g * 4], y[g * 4 + 1], y[g * 4 + 2], y[g * 4 + 3]);
+                            }
+                        }
+                    } else store_f32_slab(y, f0);
+                    if (!valid) continue;
                     if (p.acc_out) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
@@ -747,30 +1077,23 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     }
                 }
             } else
-            if (p.out_bf16 && (cend - cbeg) >= 64 && !p.no_coalesce) {
+            if (path64) {
                 // ---- coalesced path: every global access of this warp is a run of whole 128-byte lines.
                 // Each warp owns 32 accumulator rows; per 64-column slab a row is 128 B of bf16.  Rows are
                 // transposed through the warp's private swizzled staging tile so that one warp instruction moves
                 // 4 rows x 128 B instead of 32 rows x 16 B (the latter costs 32 LSU cycles per instruction and made
                 // the epilogue the bottleneck of every layer, profiles/r01_notes.md).
                 const uint32_t stg = stg_base + (uint32_t)(warp - 2) * 4096u;
-                const int srow = lane >> 3, schunk = lane & 7;
                 const unsigned long long obase = (unsigned long long)(uintptr_t)orow;
-                const unsigned long long rbase = (unsigned long long)(uintptr_t)rrow;
                 const int vflag = valid ? 1 : 0;
                 auto stage_addr = [&](int row, int chunk) { return stg + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4); };
-                auto res_to_stage = [&](int f0) {     // coalesced global -> staging
+                auto res_store = [&]() {               // registers -> staging
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int row = i * 4 + srow;
-                        const unsigned long long rp = __shfl_sync(0xffffffffu, rbase, row);
-                        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                        if (rp && (n0 + f0 + schunk * 8) < p.n_store)
-                            v = __ldg(reinterpret_cast<const uint4 *>(rp + (size_t)(n0 + f0) * 2) + schunk);
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(row, schunk)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-                    }
+                    for (int i = 0; i < 8; ++i)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(i * 4 + srow, schunk)), "r"(rres[i].x),
+                                     "r"(rres[i].y), "r"(rres[i].z), "r"(rres[i].w) : "memory");
                 };
-                if (p.res) res_to_stage(cbeg);
+                // (the first slab's residual was requested before the accumulator wait)
                 for (int f0 = cbeg; f0 < cend; f0 += 64) {
                     uint32_t v0[32], v1[32];
                     tmem_ld32(taddr + (uint32_t)f0, v0);
@@ -784,6 +1107,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         x[32 + j] = leaky ? fmaxf(a1, 0.1f * a1) : a1;
                     }
                     if (p.res) {
+                        res_store();
                         __syncwarp();
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {          // own row back from staging
@@ -801,6 +1125,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             for (int j = 0; j < 64; ++j) x[j] = fmaxf(x[j], 0.1f * x[j]);
                         }
                         __syncwarp();
+                        if (f0 + 64 < cend) res_load(f0 + 64);   // next slab's residual flies during the pack / store phase
                     }
 #pragma unroll
                     for (int c = 0; c < 8; ++c)                 // own row -> staging
@@ -819,7 +1144,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             *(reinterpret_cast<uint4 *>(op + (size_t)(n0 + f0) * 2) + schunk) = make_uint4(w0, w1, w2, w3);
                     }
                     __syncwarp();
-                    if (p.res && f0 + 64 < cend) res_to_stage(f0 + 64);   // next slab's residual in flight
                 }
             } else if (p.out_bf16 && (cend - cbeg) == 32 && !p.no_coalesce) {
                 // ---- coalesced path for 32-column slabs (BN = 32 / 64): a row is 64 B of bf16; the warp's staging
@@ -833,15 +1157,18 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 auto stage_addr = [&](int row, int chunk) { return stg + (uint32_t)row * 64u + (uint32_t)((chunk ^ ((row >> 1) & 3)) << 4); };
                 const int f0 = cbeg;
                 if (p.res) {
+                    uint4 rv4[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int row = i * 8 + srow;
-                        const unsigned long long rp = __shfl_sync(0xffffffffu, rbase, row);
-                        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    for (int i = 0; i < 4; ++i) {      // four independent loads in flight, then the stores
+                        const unsigned long long rp = __shfl_sync(0xffffffffu, rbase, i * 8 + srow);
+                        rv4[i] = make_uint4(0u, 0u, 0u, 0u);
                         if (rp && (n0 + f0 + schunk * 8) < p.n_store)
-                            v = __ldg(reinterpret_cast<const uint4 *>(rp + (size_t)(n0 + f0) * 2) + schunk);
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(row, schunk)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                            rv4[i] = __ldg(reinterpret_cast<const uint4 *>(rp + (size_t)(n0 + f0) * 2) + schunk);
                     }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(i * 8 + srow, schunk)), "r"(rv4[i].x),
+                                     "r"(rv4[i].y), "r"(rv4[i].z), "r"(rv4[i].w) : "memory");
                 }
                 uint32_t v0[32];
                 tmem_ld32(taddr + (uint32_t)f0, v0);
@@ -917,6 +1244,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             if (lane == 0) { if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_remote(tempty_bar(acc), 0); }
             if (++acc == TC_ACC) { acc = 0; acc_phase ^= 1u; }
         }
+        if (p.tma_epi && (warp & 3) == 0 && lane == 0) tma_store_wait_all();   // this group's bulk stores have completed
         if (ST && p.stats && warp == 2 && lane == 0) { p.stats[blockIdx.x * 8 + 5] = (unsigned long long)w_tfull; p.stats[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - t_begin); }
     }
 
@@ -977,15 +1305,28 @@ __global__ void __launch_bounds__(128) k_stem_tc(StemTcP p) {
     uint32_t parity = 0;
     const size_t plane = (size_t)p.H * p.W;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        const long pix = (long)tile * 128 + t;
-        const bool ok = pix < p.npix;
+        const unsigned pix = (unsigned)tile * 128u + (unsigned)t;     // npix < 2^31 (checked by the plan): 32-bit divisions
+        const bool ok = pix < (unsigned)p.npix;
         int x = 0, y = 0, n = 0;
-        if (ok) { x = (int)(pix % p.W); y = (int)((pix / p.W) % p.H); n = (int)(pix / plane); }
+        if (ok) { const unsigned row = pix / (unsigned)p.W; x = (int)(pix - row * (unsigned)p.W); n = (int)(row / (unsigned)p.H); y = (int)(row - (unsigned)n * (unsigned)p.H); }
         // ---- gather 27 taps (k = (ky*3 + kx)*3 + c), pad to 32, as bf16
         uint32_t packed[16];
         {
             const float *img = p.in + (size_t)n * 3 * plane;
             float v[32];
+            if (ok && x >= 1 && x + 1 < p.W && y >= 1 && y + 1 < p.H) {
+                // interior pixel (all but the image frame): nine row pointers, immediate offsets -1 / 0 / +1 -- the bounds-checked
+                // form below costs ~10 integer instructions per tap and made this kernel issue-bound (ncu: 627 instructions per
+                // warp and tile at 54 % issue utilisation, profiles/r02_notes.md)
+                const float *c0 = img + (size_t)y * p.W + x;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float *r1 = c0 + (size_t)c * plane, *r0 = r1 - p.W, *r2 = r1 + p.W;
+                    v[(0 * 3 + 0) * 3 + c] = __ldg(r0 - 1); v[(0 * 3 + 1) * 3 + c] = __ldg(r0); v[(0 * 3 + 2) * 3 + c] = __ldg(r0 + 1);
+                    v[(1 * 3 + 0) * 3 + c] = __ldg(r1 - 1); v[(1 * 3 + 1) * 3 + c] = __ldg(r1); v[(1 * 3 + 2) * 3 + c] = __ldg(r1 + 1);
+                    v[(2 * 3 + 0) * 3 + c] = __ldg(r2 - 1); v[(2 * 3 + 1) * 3 + c] = __ldg(r2); v[(2 * 3 + 2) * 3 + c] = __ldg(r2 + 1);
+                }
+            } else {
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
@@ -996,6 +1337,7 @@ __global__ void __launch_bounds__(128) k_stem_tc(StemTcP p) {
                     for (int c = 0; c < 3; ++c)
                         v[(ky * 3 + kx) * 3 + c] = in_img ? __ldg(img + (size_t)c * plane + (size_t)iy * p.W + ix) : 0.f;
                 }
+            }
 #pragma unroll
             for (int k = 27; k < 32; ++k) v[k] = 0.f;
 #pragma unroll
@@ -1067,7 +1409,7 @@ EncodeTiledFn encode_fn() {
 }
 
 struct TcPlan {
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmO, tmR;   // activation, filters; TMA epilogue: output, residual
     TcParams p;
     int grid;
     size_t smem;
@@ -1098,7 +1440,7 @@ int tc_conv_supported(const Layer &l, const TV &in, const TV &out, bool out_bf16
 
 static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &out, bool out_bf16, const TV &res,
                               bool res_bf16, int act2, const void *d_weights_bf16, int ldn, const float *d_bias,
-                              float alpha1, int *acc_out, int wide_rows = 0) {
+                              float alpha1, int *acc_out, int wide_rows = 0, int no_halo = 0) {
     TcPlan *plan = new TcPlan();
     memset(plan, 0, sizeof(*plan));
     TcParams &p = plan->p;
@@ -1135,38 +1477,84 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
         }
     }
     p.TW = bestTW; p.TH = 128 / bestTW;
-    p.TWlog2 = 0; while ((1 << p.TWlog2) < p.TW) ++p.TWlog2;
-    p.xt = (p.OW + p.TW - 1) / p.TW;
-    p.jt = (int)((rows + p.TH - 1) / p.TH);
-    p.nt = (l.n + BN - 1) / BN;
-    p.num_tiles = p.xt * p.jt * p.nt;
-    // CTA pairs (cta_group::2) for the wide tiles: halves the B bytes each SM has to pull through its TMA unit
+    int sms = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
     const char *cg_env = getenv("YB_TC_CG");
-    p.cg = (kind == 0 && BN == 256 && p.xt * p.jt >= 2 && !(cg_env && atoi(cg_env) == 1)) ? 2 : 1;
-    p.num_work = (p.cg == 2) ? ((p.xt * p.jt + 1) / 2) * p.nt : p.num_tiles;
-    p.a_bytes = (uint32_t)(TC_BM * BK * esz);
-    p.b_bytes = (uint32_t)((BN / p.cg) * BK * esz);   // per CTA
+    const uint32_t row_bytes = (uint32_t)(BK * esz);
+    p.cblocks = cin / BK; p.kblocks = l.size * l.size * p.cblocks;
+    p.nt = (l.n + BN - 1) / BN;
+    // everything that depends on the tile shape, for one candidate (halo or per-tap) -- returns the predicted kernel time
+    // in cycles: waves x K-blocks x max(tensor / issue time, TMA time at the ~48 B/clk/SM a streaming kernel sustains)
+    auto layout = [&](bool halo) -> double {
+        p.halo = halo ? 1 : 0;
+        if (halo) { p.TW = 8; p.TH = 16; } else { p.TW = bestTW; p.TH = 128 / bestTW; }
+        p.TWlog2 = 0; while ((1 << p.TWlog2) < p.TW) ++p.TWlog2;
+        p.xt = (p.OW + p.TW - 1) / p.TW;
+        p.jt = (int)((rows + p.TH - 1) / p.TH);
+        p.num_tiles = p.xt * p.jt * p.nt;
+        // CTA pairs (cta_group::2) for the wide tiles: halves the B bytes each SM has to pull through its TMA unit
+        p.cg = (kind == 0 && BN == 256 && p.xt * p.jt >= 2 && !(cg_env && atoi(cg_env) == 1)) ? 2 : 1;
+        p.num_work = (p.cg == 2) ? ((p.xt * p.jt + 1) / 2) * p.nt : p.num_tiles;
+        p.a_bytes = (uint32_t)(TC_BM * BK * esz);
+        p.b_bytes = (uint32_t)((BN / p.cg) * BK * esz);   // per CTA
+        // small filter matrices stay resident in shared memory for the whole kernel (one TMA pass per CTA)
+        p.bstat = (p.cg == 1 && p.nt == 1 && (size_t)p.kblocks * p.b_bytes <= 72 * 1024 && !getenv("YB_TC_NO_BSTAT")) ? 1 : 0;
+        p.bstat_bytes = p.bstat ? (uint32_t)p.kblocks * p.b_bytes : 0u;
+        p.halo_pitch = (uint32_t)(p.TW + 2) * row_bytes;
+        p.halo_bytes = halo ? (uint32_t)(p.TH + 2) * p.halo_pitch : 0u;
+        const double mma = (double)p.kk * std::max(128.0 * BN / 256.0, 60.0);       // per K-block: tensor time vs single-thread issue
+        const double a_per_kb = halo ? (double)p.halo_bytes / 9.0 : (double)p.a_bytes;
+        const double tma = (a_per_kb + (p.bstat ? 0.0 : (double)p.b_bytes)) / 48.0;
+        const int G = sms / p.cg;
+        const double waves = (double)((p.num_work + G - 1) / G);
+        return waves * p.kblocks * std::max(mma, tma);
+    };
+    // TMA epilogue: bf16 NHWC output of a stride-1 layer whose column halves are whole 64-column slabs
+    // slab width 64 (two 16 KB tiles per warp group) where the epilogue is on the critical path (few K-blocks per tile); 32
+    // (8 KB tiles: no more shared memory than the LSU staging, so the rings stay deep) for the deep-K and the BN = 64 layers
+    p.tma_epi = 0;
+    if (kind == 0 && out_bf16 && !s2 && BN >= 64 && !no_halo && !getenv("YB_TC_NO_TMA_EPI") && !getenv("YB_TC_NO_COALESCE") &&
+        (!res.base || res_bf16)) {
+        p.tma_epi = (BN >= 128 && p.kblocks <= 24) ? 64 : 32;
+        if (getenv("YB_TC_TMA_EPI_SW")) p.tma_epi = (atoi(getenv("YB_TC_TMA_EPI_SW")) == 64 && BN >= 128) ? 64 : 32;
+    }
+    const size_t ring_budget = (size_t)(p.tma_epi == 64 ? 158 : 191) * 1024;   // what is left of 227 KB beside the epilogue tiles
+    bool use_halo = false;
+    if (l.size == 3 && l.stride == 1 && l.pad == 1 && !no_halo && !getenv("YB_TC_NO_HALO") && (kind == 0 || getenv("YB_TC_HALO_ALL"))) {
+        const double t_halo = layout(true), t_tap = layout(false);
+        use_halo = t_halo < 0.97 * t_tap || getenv("YB_TC_HALO") != nullptr;
+    }
+    layout(use_halo);
     // several K-blocks per stage when they are small: the single MMA-issuing thread pays a fixed barrier round
     // trip per stage, which dominated the C<=64 layers (profiles/r01_notes.md)
     const uint32_t sps_target = getenv("YB_TC_SPS_TARGET") ? (uint32_t)atoi(getenv("YB_TC_SPS_TARGET")) : 64u * 1024u;
-    // small filter matrices stay resident in shared memory for the whole kernel (one TMA pass per CTA)
-    p.bstat = (p.cg == 1 && p.nt == 1 && (size_t)p.kblocks * p.b_bytes <= 72 * 1024 && !getenv("YB_TC_NO_BSTAT")) ? 1 : 0;
-    p.bstat_bytes = p.bstat ? (uint32_t)p.kblocks * p.b_bytes : 0u;
-    const uint32_t ring_blk = p.a_bytes + (p.bstat ? 0u : p.b_bytes);
-    p.sps = (int)std::max<uint32_t>(1, std::min<uint32_t>(4, sps_target / ring_blk));
+    const uint32_t ring_blk = (p.halo ? 0u : p.a_bytes) + (p.bstat ? 0u : p.b_bytes);
+    p.sps = (int)std::max<uint32_t>(1, std::min<uint32_t>(4, sps_target / std::max(ring_blk, 1u)));
     if (p.cg == 2) p.sps = 1;   // CTA pairs: 32 KB stages, 6 deep -- finer stages beat fewer barrier round trips here
     if (getenv("YB_TC_SPS")) p.sps = std::max(1, atoi(getenv("YB_TC_SPS")));
     if (getenv("YB_TC_SPS_CG2") && p.cg == 2) p.sps = std::max(1, atoi(getenv("YB_TC_SPS_CG2")));
     p.sps = std::min(p.sps, p.kblocks);
+    if (p.halo) p.sps = 1;      // the ring streams filter tiles only, one K-block per stage
+    const size_t fixed_smem = sizeof(float) * (size_t)p.nt * BN;
+    p.a_stages = 0; p.a_stage_bytes = 0;
+    if (p.halo) {
+        p.a_stage_bytes = (p.halo_bytes + 1023u) & ~1023u;
+        const int want = getenv("YB_TC_ASTAGES") ? atoi(getenv("YB_TC_ASTAGES")) : 3;
+        p.a_stages = std::max(2, std::min(TC_MAX_ASTAGES, want));
+        // keep at least 4 filter stages beside the activation ring
+        while (p.a_stages > 2 && !p.bstat && ring_budget - p.bstat_bytes - fixed_smem - (size_t)p.a_stages * p.a_stage_bytes < 4 * (size_t)p.b_bytes) --p.a_stages;
+    }
+    const size_t a_ring = (size_t)p.a_stages * p.a_stage_bytes;
     {   // keep the ring at least 3 stages deep
-        const size_t avail = 192 * 1024 - p.bstat_bytes - sizeof(float) * (size_t)p.nt * BN;
+        const size_t avail = ring_budget - p.bstat_bytes - fixed_smem - a_ring;
         while (p.sps > 1 && avail / ((size_t)p.sps * ring_blk) < 3) --p.sps;
     }
     p.stage_bytes = (uint32_t)p.sps * ring_blk;
     p.kbs = (p.kblocks + p.sps - 1) / p.sps;
     p.sk_T = 0; p.sk_L = 1;
     const size_t max_stages = getenv("YB_TC_MAX_STAGES") ? (size_t)atoi(getenv("YB_TC_MAX_STAGES")) : 8;
-    p.stages = (int)std::min<size_t>(max_stages, (192 * 1024 - p.bstat_bytes - sizeof(float) * (size_t)p.nt * BN) / p.stage_bytes);
+    if (p.stage_bytes == 0) p.stages = 2;   // halo + resident filters: nothing streams through the ring
+    else p.stages = (int)std::min<size_t>(max_stages, (ring_budget - p.bstat_bytes - fixed_smem - a_ring) / p.stage_bytes);
     if (p.stages < 2) fatal_throw("tc plan: tile does not fit shared memory");
     // UMMA instruction descriptor (kind::f16): D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TC_BM * p.cg) >> 4) << 24);
@@ -1175,9 +1563,9 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
     // kind::tf32: D = f32, A = B = tf32 (format 2): the tensor core reads the f32 words in place
     if (kind == 3) p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     // smem descriptor high word: SBO (8 rows * row bytes) >> 4 at bits 32..45, version 1 at bit 46, swizzle at 61..63
-    const uint32_t row_bytes = (uint32_t)(BK * esz);
-    const uint32_t layout = row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;
-    p.desc_hi = ((8u * row_bytes) >> 4) | (1u << 14) | (layout << 29);
+    const uint32_t layout_type = row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;
+    p.desc_hi = ((8u * row_bytes) >> 4) | (1u << 14) | (layout_type << 29);
+    p.desc_hi_a = (p.halo_pitch >> 4) | (1u << 14) | (layout_type << 29);   // halo A operand: 8-row groups one tile line pitch apart
     p.out = out.base; p.out_ldc = out.ldc; p.out_bf16 = out_bf16 ? 1 : 0;
     p.n = l.n;
     p.n_store = out_bf16 ? l.n : std::min<int>((l.n + 3) / 4 * 4, out.ldc);
@@ -1189,7 +1577,8 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
     p.bias = d_bias; p.act = l.activation; p.act2 = act2;
     p.dbg = getenv("YB_TC_DBG") ? atoi(getenv("YB_TC_DBG")) : 0;
     p.no_coalesce = getenv("YB_TC_NO_COALESCE") ? 1 : 0;
-    snprintf(plan->desc, sizeof(plan->desc), "%dx%dx%d -> n%d k%d s%d", l.c, l.h, l.w, l.n, l.size, l.stride);
+    snprintf(plan->desc, sizeof(plan->desc), "%dx%dx%d -> n%d k%d s%d%s%s", l.c, l.h, l.w, l.n, l.size, l.stride, p.halo ? " halo" : "",
+             p.tma_epi ? " tepi" : "");
     uint32_t cols = 32; while (cols < (uint32_t)(TC_ACC * BN)) cols *= 2;
     p.tmem_cols = cols;
 
@@ -1203,7 +1592,7 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
         // activation view (c, x_padded, merged padded rows)
         cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)in.Wp, (cuuint64_t)in.N * in.Hp};
         cuuint64_t strides[2] = {(cuuint64_t)in.ldc * esz, (cuuint64_t)in.Wp * in.ldc * esz};
-        cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)p.TW, (cuuint32_t)p.TH};
+        cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(p.halo ? p.TW + 2 : p.TW), (cuuint32_t)(p.halo ? p.TH + 2 : p.TH)};
         cuuint32_t es[3] = {1, 1, 1};
         r = enc(&plan->tmA, dtype, 3, in.base, dims, strides, box, es,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1228,17 +1617,34 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { delete plan; fatal_throw("cuTensorMapEncodeTiled(B) failed: " + std::to_string((int)r)); }
     }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    plan->tmO = plan->tmA; plan->tmR = plan->tmA;   // valid placeholders when the TMA epilogue is off
+    if (p.tma_epi) {
+        auto encode_px = [&](CUtensorMap *tm, const TV &t, const char *what) {
+            // (channels, padded x, merged padded rows) of a bf16 padded-NHWC tensor; box = one 64-channel slab of a pixel tile
+            cuuint64_t dims[3] = {(cuuint64_t)l.n, (cuuint64_t)t.Wp, (cuuint64_t)t.N * t.Hp};
+            cuuint64_t strides[2] = {(cuuint64_t)t.ldc * 2, (cuuint64_t)t.Wp * t.ldc * 2};
+            cuuint32_t box[3] = {(cuuint32_t)p.tma_epi, (cuuint32_t)p.TW, (cuuint32_t)p.TH};
+            cuuint32_t es[3] = {1, 1, 1};
+            CUresult rr = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, t.base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              p.tma_epi == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (rr != CUDA_SUCCESS) { delete plan; fatal_throw(std::string("cuTensorMapEncodeTiled(") + what + ") failed: " + std::to_string((int)rr)); }
+        };
+        encode_px(&plan->tmO, out, "output");
+        if (res.base) encode_px(&plan->tmR, res, "residual");
+    }
     plan->pdl = (getenv("YB_NO_PDL") == nullptr) ? 1 : 0;
     plan->grid = (p.cg == 2) ? 2 * std::min(p.num_work, sms / 2) : std::min(p.num_tiles, sms);
     if (getenv("YB_TC_STATS")) {
         cudaMalloc(&p.stats, sizeof(unsigned long long) * 8 * plan->grid);
         cudaMemset(p.stats, 0, sizeof(unsigned long long) * 8 * plan->grid);
     }
-    plan->smem = (size_t)p.stages * p.stage_bytes + p.bstat_bytes + 1024 /*alignment slack*/ + 8 * (2 * p.stages + 2 * TC_ACC + 1) + 16 +
-                 sizeof(float) * (size_t)p.nt * BN /*bias*/ + (size_t)p.nt * BN / 8 /*yolo mask*/ + 128 + 4096 * TC_EPI_WARPS /*epilogue staging*/;
+    plan->smem = (size_t)p.stages * p.stage_bytes + a_ring + p.bstat_bytes + 1024 /*alignment slack*/ +
+                 8 * (2 * p.stages + 2 * TC_ACC + 1 + 2 * TC_MAX_ASTAGES + 2) + 16 +
+                 sizeof(float) * (size_t)p.nt * BN /*bias*/ + (size_t)p.nt * BN / 8 /*yolo mask*/ +
+                 (p.tma_epi ? 1024 + 4 * (size_t)(128 * p.tma_epi * 2) /*TMA epilogue: [OUT | RES] tile per warp group*/
+                            : 128 + 4096 * TC_EPI_WARPS /*epilogue staging*/);
+    if (plan->smem > 227 * 1024) { delete plan; fatal_throw("tc plan: shared memory budget exceeded"); }
     if (cudaFuncSetAttribute(k_conv_tc<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(k_conv_tc<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(k_conv_tc<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
@@ -1250,8 +1656,8 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
 }
 
 void *tc_make_plan(const Layer &l, const TV &in, const TV &out, bool out_bf16, const TV &res, bool res_bf16,
-                   int act2, const void *d_weights_bf16, int ldn, const float *d_bias, int wide_rows) {
-    return make_plan_common(0, l, in, out, out_bf16, res, res_bf16, act2, d_weights_bf16, ldn, d_bias, 0.f, nullptr, wide_rows);
+                   int act2, const void *d_weights_bf16, int ldn, const float *d_bias, int wide_rows, int no_halo) {
+    return make_plan_common(0, l, in, out, out_bf16, res, res_bf16, act2, d_weights_bf16, ldn, d_bias, 0.f, nullptr, wide_rows, no_halo);
 }
 
 // FP32 convolution of the exact (INT8 / XNOR) networks on kind::tf32: f32 NHWC activations and f32 [ldn][K] weights go
@@ -1320,7 +1726,7 @@ int tc_plan_enable_ksplit(void *vp, float *ws, unsigned *flags) {
     TcParams &p = plan->p;
     const char *ev = getenv("YB_TC_KSPLIT");                 // 0: never (even when the option asks for it)
     if (ev && ev[0] == '0') return 0;
-    if (p.kind != 0 || !ws || !flags) return 0;
+    if (p.kind != 0 || !ws || !flags || p.halo) return 0;   // (the halo schedule has no K-split tail)
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1362,6 +1768,7 @@ void *tc_stem_make_plan(const Layer &l, const TV &out, const void *d_w, const fl
     p.out = out.base; p.out_ldc = out.ldc; p.w = reinterpret_cast<const __nv_bfloat16 *>(d_w); p.bias = d_bias;
     p.N = out.N; p.H = l.h; p.W = l.w; p.OHp = out.Hp; p.OWp = out.Wp; p.nf = l.n; p.act = l.activation;
     p.npix = (long)out.N * l.h * l.w;
+    if (p.npix >= (1L << 31) - 256) fatal_throw("stem plan: more than 2^31 pixels per batch");
     p.ntiles = (int)((p.npix + 127) / 128);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -1401,13 +1808,13 @@ void tc_launch(void *vp, cudaStream_t s) {
     const bool ks = plan->p.sk_T > 0 || ks_always;
     const bool st = plan->p.stats != nullptr && !ks;   // role counters: a separate instantiation (YB_TC_STATS=1)
     if (plan->p.cg == 2) {
-        if (ks) cudaLaunchKernelEx(&cfg, k_conv_tc<2, true, false>, plan->tmA, plan->tmB, plan->p);
-        else if (st) cudaLaunchKernelEx(&cfg, k_conv_tc<2, false, true>, plan->tmA, plan->tmB, plan->p);
-        else cudaLaunchKernelEx(&cfg, k_conv_tc<2, false, false>, plan->tmA, plan->tmB, plan->p);
+        if (ks) cudaLaunchKernelEx(&cfg, k_conv_tc<2, true, false>, plan->tmA, plan->tmB, plan->tmO, plan->tmR, plan->p);
+        else if (st) cudaLaunchKernelEx(&cfg, k_conv_tc<2, false, true>, plan->tmA, plan->tmB, plan->tmO, plan->tmR, plan->p);
+        else cudaLaunchKernelEx(&cfg, k_conv_tc<2, false, false>, plan->tmA, plan->tmB, plan->tmO, plan->tmR, plan->p);
     } else {
-        if (ks) cudaLaunchKernelEx(&cfg, k_conv_tc<1, true, false>, plan->tmA, plan->tmB, plan->p);
-        else if (st) cudaLaunchKernelEx(&cfg, k_conv_tc<1, false, true>, plan->tmA, plan->tmB, plan->p);
-        else cudaLaunchKernelEx(&cfg, k_conv_tc<1, false, false>, plan->tmA, plan->tmB, plan->p);
+        if (ks) cudaLaunchKernelEx(&cfg, k_conv_tc<1, true, false>, plan->tmA, plan->tmB, plan->tmO, plan->tmR, plan->p);
+        else if (st) cudaLaunchKernelEx(&cfg, k_conv_tc<1, false, true>, plan->tmA, plan->tmB, plan->tmO, plan->tmR, plan->p);
+        else cudaLaunchKernelEx(&cfg, k_conv_tc<1, false, false>, plan->tmA, plan->tmB, plan->tmO, plan->tmR, plan->p);
     }
 }
 

@@ -12,8 +12,9 @@ namespace yb {
 int tc_conv_supported(const Layer &l, const TV &in, const TV &out, bool out_bf16);
 // builds the per-layer launch state (TMA tensor maps, tile schedule); throws yb::Error on failure.
 // wide_rows: prefer wide pixel tiles (the plan will get tc_plan_fuse_yolo: NCHW plane stores in the epilogue)
+// no_halo: keep the one-TMA-box-per-tap schedule for 3x3 layers (the K-split tail only exists there)
 void *tc_make_plan(const Layer &l, const TV &in, const TV &out, bool out_bf16, const TV &res, bool res_bf16,
-                   int act2, const void *d_weights_bf16, int ldn, const float *d_bias, int wide_rows = 0);
+                   int act2, const void *d_weights_bf16, int ldn, const float *d_bias, int wide_rows = 0, int no_halo = 0);
 // kind::tf32 variant for the FP32 detection heads of the exact (INT8 / XNOR) networks: f32 in, f32 [ldn][K] weights, f32 out
 int tc_tf32_supported(const Layer &l, const TV &in, const TV &out);
 void *tc_make_plan_tf32(const Layer &l, const TV &in, const TV &out, const void *d_weights_f32, int ldn, const float *d_bias,

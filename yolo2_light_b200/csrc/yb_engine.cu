@@ -212,9 +212,6 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
         if (l.xnor) {
             any_xnor = true;
             if (!l.has_mean_arr) fatal_throw("engine: xnor layer without mean_arr -- call yb_calculate_binary_weights first");
-            if (!(l.stride == 1 && l.pad == 1))
-                fatal_throw("engine: xnor convolution with stride != 1 or pad != 1 is not supported (the reference's "
-                            "fallback for it, binarize_cpu at additionally.c:128, feeds an all-zero input)");
         }
         if (opt.qrule && !l.has_int8)
             fatal_throw("engine: -quantized rule without int8 weights -- call yb_quantinization_and_get_multipliers first");
@@ -239,6 +236,12 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
         if (ev && ev[0] == '0') return false;
         return l.xnor && l.c % 32 == 0 && l.c >= 64 && l.size == 3 && l.stride == 1 && l.pad == 1 && l.n >= 8;
     };
+
+    // XNOR layers with stride != 1 or pad != 1 never reach the bit GEMM in the reference: forward_convolutional_layer_cpu
+    // binarises the input to +-1 floats (binarize_cpu, additionally.c:128-134), swaps in the +-mean weights (binarize_weights,
+    // :113-126) and runs the ordinary im2col + gemm_nn (yolov2_forward_network.c:40-50, :204) -- out-of-image taps count 0 there,
+    // not -1.  Same here: k_binarize_pm1 + the exact-order float convolution.
+    auto xnor_fallback = [&](const Layer &l) { return l.xnor && !(l.stride == 1 && l.pad == 1); };
 
     // ---- fusion plan: conv i + same-shape shortcut i+1 whose only reader is that shortcut -------------
     std::vector<int> fused_into(nl, -1);   // conv i writes layer fused_into[i]'s output
@@ -321,7 +324,11 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
         const Layer &l = net->layers[i];
         if (l.type != YB_CONVOLUTIONAL) continue;
         const int v = conv_variant(i);
-        if (v == 1 && xnor_on_tc(l)) {
+        if (v == 1 && xnor_fallback(l)) {
+            side_ld[i] = l.c;   // +-1 floats
+            side_off[i] = act_total;
+            act_total += align_up(tv_bytes(B, l.h, l.w, side_ld[i], P, DT_F32), 1024);
+        } else if (v == 1 && xnor_on_tc(l)) {
             side_ld[i] = l.c;   // +-1 bytes
             side_off[i] = act_total;
             act_total += align_up(tv_bytes(B, l.h, l.w, side_ld[i], P, DT_S8), 1024);
@@ -341,7 +348,7 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
 
     for (int i = 0; i < nl; ++i) {   // +-1 activation buffers: borders are -1 (out-of-image taps count as -1)
         const Layer &l = net->layers[i];
-        if (l.type == YB_CONVOLUTIONAL && conv_variant(i) == 1 && xnor_on_tc(l))
+        if (l.type == YB_CONVOLUTIONAL && conv_variant(i) == 1 && xnor_on_tc(l) && !xnor_fallback(l))
             CUDA_OK(cudaMemsetAsync(e->act_arena + side_off[i], 0xFF, tv_bytes(B, l.h, l.w, side_ld[i], P, DT_S8), e->stream));
     }
     e->in0 = make_tv(e->act_arena + in0_off, B, net->h, net->w, net->c, net->c, P, ADT, 0);
@@ -459,6 +466,15 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                             dst[(ADT == DT_F32 ? (size_t)c * taps + t : (size_t)t * l.c + c) * w.ldw + f] =
                                 l.weights[((size_t)f * l.c + c) * taps + t];
             }
+        } else if (v == 1 && xnor_fallback(l)) {
+            // f32 [K][ldw], K in the reference's (c, ky, kx) order: +mean where w > 0, -mean otherwise (binarize_weights)
+            w.ldw = (int)align_up(l.n, 64);
+            w.w_f32 = reserve(sizeof(float) * (size_t)K * w.ldw);
+            float *dst = reinterpret_cast<float *>(&hostw[w.w_f32]);
+            for (int f = 0; f < l.n; ++f)
+                for (int c = 0; c < l.c; ++c)
+                    for (int t = 0; t < taps; ++t)
+                        dst[((size_t)c * taps + t) * w.ldw + f] = l.weights[((size_t)f * l.c + c) * taps + t] > 0 ? l.mean_arr[f] : -l.mean_arr[f];
         } else if (v == 1 && xnor_on_tc(l)) {
             // +-1 bytes [ldn][taps][C]: +1 where w > 0, -1 otherwise; padded filter rows stay 0
             w.cpad = l.c;
@@ -617,9 +633,12 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                     const bool fuse_yolo = opt.fuse && fused_into[i] < 0 && odt == DT_F32 && i + 1 < nl &&
                                            net->layers[i + 1].type == YB_YOLO && cons[i].size() == 1 && cons[i][0] == i + 1 &&
                                            e->d_final[i + 1] && !getenv("YB_NO_YOLO_FUSE");
+                    const char *ks_env = getenv("YB_TC_KSPLIT");   // 1: on without the option (A/B runs)
+                    const bool want_ksplit = opt.ksplit || (ks_env && ks_env[0] == '1');
                     void *plan = tc_make_plan(l, tin, tout, odt == DT_BF16, res, rdt == DT_BF16, act2,
                                               e->w_arena + cw[i].w_bf16, cw[i].ldn,
-                                              reinterpret_cast<const float *>(e->w_arena + cw[i].bias), fuse_yolo ? 1 : 0);
+                                              reinterpret_cast<const float *>(e->w_arena + cw[i].bias), fuse_yolo ? 1 : 0,
+                                              want_ksplit ? 1 : 0);
                     e->tc_plans.push_back(plan);
                     if (!e->ksplit_ws) {
                         int sms = 148;
@@ -629,8 +648,7 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                         CUDA_OK(cudaMemset(e->ksplit_flags, 0, tc_ksplit_flag_bytes(sms)));
                     }
                     ++e->n_tc;
-                    const char *ks_env = getenv("YB_TC_KSPLIT");   // 1: on without the option (A/B runs)
-                    if (opt.ksplit || (ks_env && ks_env[0] == '1'))
+                    if (want_ksplit)
                         e->n_ksplit += tc_plan_enable_ksplit(plan, e->ksplit_ws, e->ksplit_flags);
                     if (fuse_yolo) {
                         tc_plan_fuse_yolo(plan, e->d_final[i + 1], net->layers[i + 1].classes);
@@ -661,6 +679,20 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                 }
             } else if (v == 1) {
                 if (in_dt != DT_F32 || odt != DT_F32) fatal_throw("engine: xnor path needs f32 activations");
+                if (xnor_fallback(l)) {
+                    TV pm1 = make_tv(e->act_arena + side_off[i], B, l.h, l.w, l.c, l.c, P, DT_F32, 0);
+                    const int gb = grid_for((long)B * l.h * l.w * l.c);
+                    e->ops.push_back(Op{OP_BINARIZE, i, [tin, pm1, gb](cudaStream_t s) { k_binarize_pm1<<<gb, 256, 0, s>>>(tin, pm1); }});
+                    ConvP p{};
+                    p.in = pm1; p.out = tout; p.res = TV{};
+                    p.w = e->w_arena + cw[i].w_f32;
+                    p.bias = reinterpret_cast<const float *>(e->w_arena + cw[i].bias);
+                    p.n = l.n; p.ldw = cw[i].ldw; p.size = l.size; p.stride = l.stride; p.pad = l.pad;
+                    p.act = l.activation; p.act2 = ACT_LINEAR; p.K = l.size * l.size * l.c; p.M = M;
+                    dim3 grid((unsigned)((M + 63) / 64), (unsigned)((l.n + 63) / 64));
+                    e->ops.push_back(Op{OP_CONV_SIMT, i, [p, grid](cudaStream_t s) { k_conv_simt<float, float, float, true><<<grid, 256, 0, s>>>(p); }});
+                    break;
+                }
                 int32_t *cnt_dbg = nullptr;
                 if (opt.keep_counts) {
                     e->counts_count[i] = (size_t)B * l.n * l.out_h * l.out_w;
@@ -764,7 +796,7 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
             // order as max-pool + quantise / binarise; the pooled f32 tensor never goes to HBM)
             if (opt.fuse && in_dt == DT_F32 && i + 1 < nl && cons[i].size() == 1 && cons[i][0] == i + 1 &&
                 net->layers[i + 1].type == YB_CONVOLUTIONAL && conv_variant(i + 1) != 0 && side_off[i + 1] != (size_t)-1 &&
-                !getenv("YB_NO_POOL_FUSE")) {
+                !xnor_fallback(net->layers[i + 1]) && !getenv("YB_NO_POOL_FUSE")) {
                 const Layer &c = net->layers[i + 1];
                 const int v = conv_variant(i + 1);
                 if (v == 2) {

@@ -349,6 +349,18 @@ __global__ void k_binarize(TV in, TV bits /* C = words per pixel */) {
     }
 }
 
+// binarize_cpu (additionally.c:128-134): x > 0 ? +1 : -1 as floats -- the input of the XNOR layers that take the reference's
+// float-GEMM fallback (stride != 1 or pad != 1).  The zero border of the destination stays zero (im2col's padding value).
+static __global__ void k_binarize_pm1(TV in, TV out) {
+    const long total = (long)in.N * in.H * in.W * in.C;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % in.C);
+        const long px = i / in.C;
+        const int x = (int)(px % in.W), y = (int)((px / in.W) % in.H), n = (int)(px / ((long)in.W * in.H));
+        tv_px<float>(out, n, y, x)[c] = tv_px<float>(in, n, y, x)[c] > 0.f ? 1.f : -1.f;
+    }
+}
+
 struct XnorP {
     TV bits;                  // input bits, C = words per pixel (CW)
     TV out;                   // f32
