@@ -422,3 +422,32 @@ def test_xnor_stride_pad_fallback_matches_reference(workdir):
             assert util.bits_equal(got, exp), (b, i, float(np.abs(got - exp).max()))
         for i, o in net.detection_outputs().items():
             assert util.rel_l2(o[b], rnet.output(i)[0].reshape(o[b].shape)) <= 1e-3
+
+
+# ---- stem + max-pool + quantise / binarise in one kernel (exact nets) ------------------------------------------------------
+@pytest.mark.parametrize("builder,w,h,q", [(cfgs.yolov3_tiny, 64, 64, 1), (cfgs.tiny_yolo_obj_xnor, 64, 64, 0), (cfgs.yolov3_tiny, 96, 64, 1)])
+def test_fused_stem_pool_is_bit_identical_to_the_three_kernels(builder, w, h, q, workdir):
+    """k_stem_pool (layers 0-1 + the integer layer's input conversion; full-width models: the stem has 16 filters) against the
+    unfused plan: the first integer convolution, every later layer and the detections are bit-identical; layers 0 and 1 are
+    no longer materialised."""
+    import yolo2_light_b200 as yb
+    B = 3
+    secs = builder(w, h)
+    cfg = cfgs.write_cfg(secs, os.path.join(workdir, f"sp_{builder.__name__}_{w}x{h}.cfg"))
+    wts = cfgs.write_weights(secs, os.path.join(workdir, f"sp_{builder.__name__}_{w}x{h}.weights"), seed=61)
+    x = cfgs.synthetic_images(B, 3, h, w, seed=62)
+    nets = []
+    for fuse in (0, 1):
+        net = yb.load_network(cfg, wts, batch=B, quantized=q)
+        net.set_option("fuse", fuse)
+        net.set_option("keep_counts", 1)
+        net.predict(x, quantized=bool(q))
+        nets.append(net)
+    a, b = nets
+    assert b.last_launches() <= a.last_launches() - 3        # stem, max-pool and quantise / binarise became one launch
+    with pytest.raises(yb.YbError):
+        b.fetch_layer(0, quantized=bool(q))
+    assert np.array_equal(a.fetch_counts(2, quantized=bool(q)), b.fetch_counts(2, quantized=bool(q)))
+    assert util.bits_equal(a.fetch_layer(2, quantized=bool(q)), b.fetch_layer(2, quantized=bool(q)))
+    for i, o in a.detection_outputs().items():
+        assert util.bits_equal(o, b.layer_output(i)), (builder.__name__, i)

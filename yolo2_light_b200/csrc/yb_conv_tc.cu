@@ -85,6 +85,10 @@ struct TcParams {
     // bf16 into a 128B-swizzled shared-memory tile and one thread stores it with cp.async.bulk.tensor; the shortcut residual
     // comes in the same way (TMA load + mbarrier).  No shuffles, no staging transposes, no LSU global traffic, ~100 registers.
     int tma_epi;
+    // epi_alt (with tma_epi, BN <= 128): the two groups of four epilogue warps take ALTERNATE tiles (group g: accumulator g, all
+    // BN columns) instead of half the columns of every tile -- two tiles are in the epilogue at once; the per-tile epilogue of the
+    // small tiles is a latency chain (TMEM load -> math -> barrier -> store), not a throughput problem.
+    int epi_alt;
     int sps;                                  // K-blocks per pipeline stage (amortises the per-stage barrier round trip)
     int kbs;                                  // pipeline stages per work item = ceil(kblocks / sps)
     // K-split tail (wave quantisation): the last num_work % G work items ("tail") are cut along K into slices of sk_L
@@ -258,6 +262,12 @@ __device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
+__device__ __forceinline__ void umma2_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
 __device__ __forceinline__ void umma2_commit_both(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"((uint16_t)3) : "memory");
@@ -317,7 +327,10 @@ __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
 // KS: compiled with the K-split tail schedule (TcParams::sk_T); the KS = false instantiations carry none of its code.
 // ST: compiled with the per-role cycle counters of YB_TC_STATS=1 (diagnostic); the production instantiations (ST = false)
 // contain no clock64() reads -- the single-thread producer / MMA roles are issue-bound on the BN <= 128 layers.
-template <int CG, bool KS, bool ST>
+// EPI: which epilogue family is compiled in -- 0: LSU stores, float kinds (bf16 / f32 heads / fused [yolo]); 1: TMA epilogue
+// (bf16 tiles stored with cp.async.bulk.tensor); 2: the integer kinds (kind::i8 requantising and XNOR-as-+-1 epilogues).  One
+// kernel with all three spilled ~1.5 KB per thread (168 registers is the cap for 320 threads) and cost the LSU layers 10-25 %.
+template <int CG, bool KS, bool ST, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
           const __grid_constant__ CUtensorMap tmR, const TcParams p) {
@@ -350,13 +363,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // full: one arrival (the leader's expect_tx; the peer's bytes are covered by the transaction count);
         // tempty: one arrival per epilogue warp (of both CTAs when paired)
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < TC_ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), CG * TC_EPI_WARPS); }
+        for (int a = 0; a < TC_ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), CG * (p.epi_alt ? TC_EPI_WARPS / 2 : TC_EPI_WARPS)); }
         mbar_init(bstat_bar, 1);
         for (int s = 0; s < TC_MAX_ASTAGES; ++s) { mbar_init(fullA_bar(s), 1); mbar_init(emptyA_bar(s), 1); }
         mbar_init(resfull_bar(0), 1); mbar_init(resfull_bar(1), 1);
         if (p.tma_epi) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
-            if (p.res) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
+            if (p.res && EPI == 1) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -530,7 +543,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     const uint64_t adesc = ((uint64_t)ahi << 32) | (uint64_t)(alo + 2u * (uint32_t)k);
                     const uint64_t bdesc = ((uint64_t)bhi << 32) | (uint64_t)(blo + 2u * (uint32_t)k);
                     const uint32_t accum = (k == 0) ? (uint32_t)(first != 0u) : 1u;
-                    if constexpr (CG == 2) umma2_bf16(d_tmem, adesc, bdesc, idesc, accum);
+                    if constexpr (CG == 2 && KIND == 1) umma2_i8(d_tmem, adesc, bdesc, idesc, accum);
+                    else if constexpr (CG == 2) umma2_bf16(d_tmem, adesc, bdesc, idesc, accum);
                     else if constexpr (KIND == 3) umma_tf32(d_tmem, adesc, bdesc, idesc, accum);
                     else if constexpr (KIND == 1) umma_i8(d_tmem, adesc, bdesc, idesc, accum);
                     else umma_bf16(d_tmem, adesc, bdesc, idesc, accum);
@@ -665,10 +679,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 else if (p.kk == 2) mma_role(kind_c, std::integral_constant<int, 2>{});
                 else mma_role(kind_c, std::integral_constant<int, 1>{});
             };
-            if constexpr (CG == 2) by_kk(std::integral_constant<int, 0>{});
+            if constexpr (EPI == 2) by_kk(std::integral_constant<int, 1>{});
+            else if constexpr (CG == 2 || EPI == 1) by_kk(std::integral_constant<int, 0>{});
             else if (p.kind == 0) by_kk(std::integral_constant<int, 0>{});
-            else if (p.kind == 3) by_kk(std::integral_constant<int, 3>{});
-            else by_kk(std::integral_constant<int, 1>{});
+            else by_kk(std::integral_constant<int, 3>{});
         }
     } else {
         // ======================= epilogue (warps 2..9) =======================
@@ -677,17 +691,20 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // was epilogue-bound on exactly that, profiles/r01_notes.md).
         const int q = warp & 3;                   // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;         // which half of the columns this warp owns
-        const int cbeg = (p.BN >= 64) ? half * (p.BN >> 1) : 0;
-        const int cend = (p.BN >= 64) ? cbeg + (p.BN >> 1) : (half == 0 ? p.BN : 0);
+        const int cbeg = p.epi_alt ? 0 : (p.BN >= 64) ? half * (p.BN >> 1) : 0;
+        const int cend = p.epi_alt ? p.BN : (p.BN >= 64) ? cbeg + (p.BN >> 1) : (half == 0 ? p.BN : 0);
         const int r = q * 32 + lane;              // accumulator row == pixel within the tile
         const int tx = r & (p.TW - 1), ty = r >> p.TWlog2;
         const bool leaky = p.act == ACT_LEAKY, leaky2 = p.act2 == ACT_LEAKY;
-        int acc = 0; uint32_t acc_phase = 0;
+        int acc = p.epi_alt ? half : 0; uint32_t acc_phase = 0;
         uint32_t epi_res_phase = 0;               // TMA epilogue: parity of this group's residual barrier
+        bool res_requested = false;               // TMA epilogue: the residual tile of the slab about to be processed is on its way
+        int tile_cnt = 0;
         long long w_tfull = 0; const long long t_begin = ST ? clock64() : 0;
         TcSched sch = sched_init<KS>(p, w_first, w_step);
         int w, seg0, seg1;
         while (sched_next<KS>(sch, w, seg0, seg1)) {
+            if (p.epi_alt && ((tile_cnt++ & 1) != half)) continue;   // the other group's tile
             // K-split tail: a segment that stops short of the work item's last stage only publishes its raw accumulator;
             // the segment that ends the work item adds the npart partials of the CTAs (pairs) gA .. unit-1 before it
             const bool seg_partial = KS && seg1 < p.kbs;
@@ -717,34 +734,16 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             };
             // the staged bf16 store paths fetch their own residual, the integer / tf32 kinds never have one: rv[] is only
             // prefetched for the per-thread store path (f32 heads, YB_TC_NO_COALESCE)
-            const bool own_res = (p.out_bf16 && ((cend - cbeg) >= 64 || (cend - cbeg) == 32) && !p.no_coalesce) || p.kind != 0 || !p.res || p.tma_epi;
+            const bool own_res = EPI != 0 || (p.out_bf16 && ((cend - cbeg) >= 64 || (cend - cbeg) == 32) && !p.no_coalesce) || !p.res;
             if (!own_res) {
                 if (cbeg < cend) load_res(cbeg, rv[0]);
                 if (cend - cbeg > 32) load_res(cbeg + 32, rv[1]);
             }
 
-            // The 64-column staged store path is decided here, before the accumulator wait, so that its first residual fetch
-            // overlaps the wait.  Residual (fused shortcut): 8 independent 16-byte loads per thread go out TOGETHER into
-            // registers (rres) and only later into the staging tile.  (Round 1 stored every value right behind its load inside
-            // one asm-volatile sequence: eight fully serialised global-load latencies per 64-column slab, ~5 k cycles -- that,
-            // not the tensor pipe or TMA, bounded every shortcut-fused 3x3 layer; profiles/r02_notes.md.)
-            const bool path64 = !seg_partial && !p.tma_epi && p.kind != 1 && p.kind != 2 && p.out_bf16 && (cend - cbeg) >= 64 && !p.no_coalesce;
-            const int srow = lane >> 3, schunk = lane & 7;
-            const unsigned long long rbase = (unsigned long long)(uintptr_t)rrow;
-            uint4 rres[8];
-            auto res_load = [&](int f0) {          // coalesced global -> registers (whole 128-byte lines per 8 lanes)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const unsigned long long rp = __shfl_sync(0xffffffffu, rbase, i * 4 + srow);
-                    rres[i] = make_uint4(0u, 0u, 0u, 0u);
-                    if (rp && (n0 + f0 + schunk * 8) < p.n_store)
-                        rres[i] = __ldg(reinterpret_cast<const uint4 *>(rp + (size_t)(n0 + f0) * 2) + schunk);
-                }
-            };
-            if (path64 && p.res) res_load(cbeg);
+            const bool path64 = EPI == 0 && !seg_partial && p.out_bf16 && (cend - cbeg) >= 64 && !p.no_coalesce;
 
             // (the TMA epilogue requests its first residual tile before this wait and waits itself)
-            const bool tfull_waited = !p.tma_epi;
+            const bool tfull_waited = EPI != 1;
             if (tfull_waited) {
                 if constexpr (ST) { const long long c0 = clock64(); mbar_wait(tfull_bar(acc), acc_phase, 3); w_tfull += clock64() - c0; }
                 else mbar_wait(tfull_bar(acc), acc_phase, 3);
@@ -917,7 +916,32 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 __syncwarp();
             };
 
-            if (p.tma_epi) {
+            // ---- TMA store of one 32-column f32 slab (integer kinds): the group's [128 pixels][32 floats] tile, 128-byte rows with
+            // the 128B swizzle, written by one thread per row and stored by one cp.async.bulk.tensor
+            auto tma_store_f32_slab = [&](const float (&y)[32], int f0) {
+                const int g = half;
+                const uint32_t out_tile = stg_base + (uint32_t)g * 16384u;
+                const bool boss = (q == 0) && (lane == 0);
+                const uint32_t rsw = (uint32_t)(r & 7), row_off = (uint32_t)r * 128u;
+                if (boss) tma_store_wait_read0();                      // the previous store has finished reading the tile
+                named_bar_sync(1 + g, 128);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    uint32_t o0 = __float_as_uint(y[c * 4 + 0]), o1 = __float_as_uint(y[c * 4 + 1]);
+                    uint32_t o2 = __float_as_uint(y[c * 4 + 2]), o3 = __float_as_uint(y[c * 4 + 3]);
+                    if (!valid) { o0 = o1 = o2 = o3 = 0u; }           // border / padding rows inside the tensor stay zero
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(out_tile + row_off + (((uint32_t)c ^ rsw) << 4)),
+                                 "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                named_bar_sync(1 + g, 128);
+                if (boss) {
+                    tma_store_3d(&tmO, out_tile, n0 + f0, (m % p.xt) * p.TW + 1, (m / p.xt) * p.TH);
+                    tma_store_commit();
+                }
+            };
+
+            if constexpr (EPI == 1) {
                 // ---- TMA epilogue.  Group g = the four warps that own column half `half` (128 threads, named barrier 1 + half);
                 // per slab of SW = 64 (or 32) columns: [OUT tile][RES tile], both [128 pixel rows][SW * 2 bytes] with the swizzle of
                 // the tensor maps -- 16-byte chunk c of row r at r*128 + ((c ^ (r & 7)) << 4) for 128-byte rows, at r*64 +
@@ -933,10 +957,16 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     const uint32_t rsw = (NV == 2) ? (uint32_t)(r & 7) : (uint32_t)((r >> 1) & 3);
                     const uint32_t row_off = (uint32_t)r * rowb;
                     const bool has_res = p.res != nullptr;
-                    if (has_res && boss) {                                // first slab's residual: flies under the accumulator wait
+                    // residual tiles are requested one slab AHEAD, across tile boundaries (the next work item of this group is
+                    // known: w + step): the TMA latency hides behind the store phase of this slab and the accumulator wait of the next
+                    const int wstep_g = p.epi_alt ? 2 * w_step : w_step;
+                    auto request_res = [&](int w_, int f_) {
+                        const int m_ = (CG == 2) ? 2 * (w_ / p.nt) + (int)rank : w_ / p.nt;
                         mbar_arrive_expect_tx(resfull_bar(g), tile_bytes);
-                        tma_load_3d(res_tile, &tmR, resfull_bar(g), n0 + cbeg, x0 + 1, J0);
-                    }
+                        tma_load_3d(res_tile, &tmR, resfull_bar(g), (w_ % p.nt) * p.BN + f_, (m_ % p.xt) * p.TW + 1, (m_ / p.xt) * p.TH);
+                    };
+                    if (has_res && boss && !res_requested) request_res(w, cbeg);   // very first slab of this group
+                    res_requested = true;
                     if (!tfull_waited) {
                         if constexpr (ST) { const long long c0 = clock64(); mbar_wait(tfull_bar(acc), acc_phase, 3); w_tfull += clock64() - c0; }
                         else mbar_wait(tfull_bar(acc), acc_phase, 3);
@@ -976,9 +1006,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         // the previous slab's TMA store must have finished READING the OUT tile before it is overwritten
                         if (boss) tma_store_wait_read0();
                         named_bar_sync(1 + g, 128);
-                        if (has_res && boss && f0 + SW < cend) {           // everybody is done with the RES tile: request the next one
-                            mbar_arrive_expect_tx(resfull_bar(g), tile_bytes);
-                            tma_load_3d(res_tile, &tmR, resfull_bar(g), n0 + f0 + SW, x0 + 1, J0);
+                        if (has_res && boss) {                             // everybody is done with the RES tile: request the next one
+                            if (f0 + SW < cend) request_res(w, f0 + SW);
+                            else if (w + wstep_g < p.num_work) request_res(w + wstep_g, cbeg);
                         }
 #pragma unroll
                         for (int c = 0; c < 4 * NV; ++c) {                 // own row -> OUT tile (border / padding rows: zeros)
@@ -1001,10 +1031,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 };
                 if (p.tma_epi == 64) slabs(std::integral_constant<int, 2>{});
                 else slabs(std::integral_constant<int, 1>{});
-            } else
-            if (seg_partial) {
-                // accumulator already published above
-            } else
+            } else if constexpr (EPI == 2) {
             if (p.kind == 2) {
                 // ---- XNOR as +-1 int8: acc == 2*count - K (exact); out = act((float)acc * mean + bias) in the reference's
                 // float op order (additionally.c:1531, yolov2_forward_network.c:243-261)
@@ -1029,7 +1056,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                                 *reinterpret_cast<float4 *>(orow_f + n0 + f0 + g * 4) = make_float4(y[g * 4], y[g * 4 + 1], y[g * 4 + 2], y[g * 4 + 3]);
                             }
                         }
-                    } else store_f32_slab(y, f0);
+                    } else if (p.tma_epi) tma_store_f32_slab(y, f0);
+                    else store_f32_slab(y, f0);
                     if (!valid) continue;
                     if (p.acc_out) {
 #pragma unroll
@@ -1066,7 +1094,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                                 *reinterpret_cast<float4 *>(orow_f + n0 + f0 + g * 4) = make_float4(y[g * 4], y[g * 4 + 1], y[g * 4 + 2], y[g * 4 + 3]);
                             }
                         }
-                    } else store_f32_slab(y, f0);
+                    } else if (p.tma_epi) tma_store_f32_slab(y, f0);
+                    else store_f32_slab(y, f0);
                     if (!valid) continue;
                     if (p.acc_out) {
 #pragma unroll
@@ -1076,6 +1105,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         }
                     }
                 }
+            }
+            } else {
+            if (seg_partial) {
+                // accumulator already published above
             } else
             if (path64) {
                 // ---- coalesced path: every global access of this warp is a run of whole 128-byte lines.
@@ -1084,16 +1117,23 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 // 4 rows x 128 B instead of 32 rows x 16 B (the latter costs 32 LSU cycles per instruction and made
                 // the epilogue the bottleneck of every layer, profiles/r01_notes.md).
                 const uint32_t stg = stg_base + (uint32_t)(warp - 2) * 4096u;
+                const int srow = lane >> 3, schunk = lane & 7;
                 const unsigned long long obase = (unsigned long long)(uintptr_t)orow;
+                const unsigned long long rbase = (unsigned long long)(uintptr_t)rrow;
                 const int vflag = valid ? 1 : 0;
                 auto stage_addr = [&](int row, int chunk) { return stg + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4); };
-                auto res_store = [&]() {               // registers -> staging
+                auto res_to_stage = [&](int f0) {     // coalesced global -> staging
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(i * 4 + srow, schunk)), "r"(rres[i].x),
-                                     "r"(rres[i].y), "r"(rres[i].z), "r"(rres[i].w) : "memory");
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = i * 4 + srow;
+                        const unsigned long long rp = __shfl_sync(0xffffffffu, rbase, row);
+                        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                        if (rp && (n0 + f0 + schunk * 8) < p.n_store)
+                            v = __ldg(reinterpret_cast<const uint4 *>(rp + (size_t)(n0 + f0) * 2) + schunk);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(row, schunk)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                    }
                 };
-                // (the first slab's residual was requested before the accumulator wait)
+                if (p.res) res_to_stage(cbeg);
                 for (int f0 = cbeg; f0 < cend; f0 += 64) {
                     uint32_t v0[32], v1[32];
                     tmem_ld32(taddr + (uint32_t)f0, v0);
@@ -1107,7 +1147,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         x[32 + j] = leaky ? fmaxf(a1, 0.1f * a1) : a1;
                     }
                     if (p.res) {
-                        res_store();
                         __syncwarp();
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {          // own row back from staging
@@ -1125,7 +1164,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             for (int j = 0; j < 64; ++j) x[j] = fmaxf(x[j], 0.1f * x[j]);
                         }
                         __syncwarp();
-                        if (f0 + 64 < cend) res_load(f0 + 64);   // next slab's residual flies during the pack / store phase
                     }
 #pragma unroll
                     for (int c = 0; c < 8; ++c)                 // own row -> staging
@@ -1144,6 +1182,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             *(reinterpret_cast<uint4 *>(op + (size_t)(n0 + f0) * 2) + schunk) = make_uint4(w0, w1, w2, w3);
                     }
                     __syncwarp();
+                    if (p.res && f0 + 64 < cend) res_to_stage(f0 + 64);   // next slab's residual in flight
                 }
             } else if (p.out_bf16 && (cend - cbeg) == 32 && !p.no_coalesce) {
                 // ---- coalesced path for 32-column slabs (BN = 32 / 64): a row is 64 B of bf16; the warp's staging
@@ -1157,18 +1196,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 auto stage_addr = [&](int row, int chunk) { return stg + (uint32_t)row * 64u + (uint32_t)((chunk ^ ((row >> 1) & 3)) << 4); };
                 const int f0 = cbeg;
                 if (p.res) {
-                    uint4 rv4[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {      // four independent loads in flight, then the stores
-                        const unsigned long long rp = __shfl_sync(0xffffffffu, rbase, i * 8 + srow);
-                        rv4[i] = make_uint4(0u, 0u, 0u, 0u);
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = i * 8 + srow;
+                        const unsigned long long rp = __shfl_sync(0xffffffffu, rbase, row);
+                        uint4 v = make_uint4(0u, 0u, 0u, 0u);
                         if (rp && (n0 + f0 + schunk * 8) < p.n_store)
-                            rv4[i] = __ldg(reinterpret_cast<const uint4 *>(rp + (size_t)(n0 + f0) * 2) + schunk);
+                            v = __ldg(reinterpret_cast<const uint4 *>(rp + (size_t)(n0 + f0) * 2) + schunk);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(row, schunk)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
                     }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(i * 8 + srow, schunk)), "r"(rv4[i].x),
-                                     "r"(rv4[i].y), "r"(rv4[i].z), "r"(rv4[i].w) : "memory");
                 }
                 uint32_t v0[32];
                 tmem_ld32(taddr + (uint32_t)f0, v0);
@@ -1238,13 +1274,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         finish(v0, rv[0], f0);
                 }
             }
+            }
             tc_fence_before();
             // all epilogue threads (of both CTAs) hand the accumulator back to the (leader's) MMA warp
             __syncwarp();
             if (lane == 0) { if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_remote(tempty_bar(acc), 0); }
-            if (++acc == TC_ACC) { acc = 0; acc_phase ^= 1u; }
+            if (p.epi_alt) acc_phase ^= 1u;       // this group always works on accumulator `half`
+            else if (++acc == TC_ACC) { acc = 0; acc_phase ^= 1u; }
         }
-        if (p.tma_epi && (warp & 3) == 0 && lane == 0) tma_store_wait_all();   // this group's bulk stores have completed
+        if ((EPI == 1 || (EPI == 2 && p.tma_epi)) && (warp & 3) == 0 && lane == 0) tma_store_wait_all();   // this group's bulk stores have completed
         if (ST && p.stats && warp == 2 && lane == 0) { p.stats[blockIdx.x * 8 + 5] = (unsigned long long)w_tfull; p.stats[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - t_begin); }
     }
 
@@ -1282,6 +1320,7 @@ __global__ void __launch_bounds__(128) k_stem_tc(StemTcP p) {
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_slot;
     __shared__ float bias_s[32];
+    __shared__ unsigned long long optr[128];   // global address of every pixel's output row of the current tile (0: none)
     const int t = threadIdx.x, warp = t >> 5;
     const uint32_t a_addr = smem_u32(a_tile), b_addr = smem_u32(b_tile), bar = smem_u32(&mma_bar);
     if (t < 32) bias_s[t] = (t < p.nf) ? p.bias[t] : 0.f;
@@ -1365,8 +1404,35 @@ __global__ void __launch_bounds__(128) k_stem_tc(StemTcP p) {
         uint32_t acc[32];
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), acc);
         tmem_ld_wait();
-        if (ok) {
-            char *orow = p.out + ((size_t)(n * p.OHp + y + 1) * p.OWp + x + 1) * (size_t)p.out_ldc * 2;
+        char *orow = ok ? p.out + ((size_t)(n * p.OHp + y + 1) * p.OWp + x + 1) * (size_t)p.out_ldc * 2 : nullptr;
+        if (p.nf == 32) {
+            // 64-byte pixel rows: stage the tile in shared memory (the A tile is free once the MMA has retired) and write it out
+            // 512 contiguous bytes per warp instruction.  One STG.128 per thread on its own row touched 16 lines per instruction:
+            // the L1 store wavefronts, not HBM, bounded this kernel (ncu: l1tex 74 % busy at 2.2 TB/s, profiles/r02_notes.md).
+            uint4 o[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float r[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float a = __uint_as_float(acc[g * 8 + j]) + bias_s[g * 8 + j];
+                    r[j] = (p.act == ACT_LEAKY) ? fmaxf(a, 0.1f * a) : a;
+                }
+                o[g] = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4 *>(a_tile + t * 64 + ((g ^ ((t >> 1) & 3)) << 4)) = o[g];
+            optr[t] = (unsigned long long)(uintptr_t)orow;
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int j = t + 128 * k, px = j >> 2, part = j & 3;
+                const unsigned long long dst = optr[px];
+                if (dst)
+                    *reinterpret_cast<uint4 *>(dst + (unsigned long long)(part * 16)) =
+                        *reinterpret_cast<const uint4 *>(a_tile + px * 64 + ((part ^ ((px >> 1) & 3)) << 4));
+            }
+        } else if (ok) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 if (g * 8 >= p.nf) break;
@@ -1493,7 +1559,8 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
         p.jt = (int)((rows + p.TH - 1) / p.TH);
         p.num_tiles = p.xt * p.jt * p.nt;
         // CTA pairs (cta_group::2) for the wide tiles: halves the B bytes each SM has to pull through its TMA unit
-        p.cg = (kind == 0 && BN == 256 && p.xt * p.jt >= 2 && !(cg_env && atoi(cg_env) == 1)) ? 2 : 1;
+        p.cg = ((kind == 0 || ((kind == 1 || kind == 2) && !getenv("YB_TC_I8_CG1"))) && BN == 256 && p.xt * p.jt >= 2 &&
+                !(cg_env && atoi(cg_env) == 1)) ? 2 : 1;
         p.num_work = (p.cg == 2) ? ((p.xt * p.jt + 1) / 2) * p.nt : p.num_tiles;
         p.a_bytes = (uint32_t)(TC_BM * BK * esz);
         p.b_bytes = (uint32_t)((BN / p.cg) * BK * esz);   // per CTA
@@ -1513,14 +1580,21 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
     // slab width 64 (two 16 KB tiles per warp group) where the epilogue is on the critical path (few K-blocks per tile); 32
     // (8 KB tiles: no more shared memory than the LSU staging, so the rings stay deep) for the deep-K and the BN = 64 layers
     p.tma_epi = 0;
-    if (kind == 0 && out_bf16 && !s2 && BN >= 64 && !no_halo && !getenv("YB_TC_NO_TMA_EPI") && !getenv("YB_TC_NO_COALESCE") &&
+    const bool i8kind = kind == 1 || kind == 2;
+    if (kind == 0 && out_bf16 && !s2 && BN >= 32 && !no_halo && !getenv("YB_TC_NO_TMA_EPI") && !getenv("YB_TC_NO_COALESCE") &&
         (!res.base || res_bf16)) {
-        p.tma_epi = (BN >= 128 && p.kblocks <= 24) ? 64 : 32;
+        p.tma_epi = (BN >= 128 && p.kblocks <= 24) ? 64 : 32;   // measured per layer class (profiles/r02_notes.md)
         if (getenv("YB_TC_TMA_EPI_SW")) p.tma_epi = (atoi(getenv("YB_TC_TMA_EPI_SW")) == 64 && BN >= 128) ? 64 : 32;
     }
+    // integer kinds: f32 slabs of 32 columns (128-byte rows) stored by TMA; the raw-accumulator dump (tests) keeps the LSU path
+    if (i8kind && !s2 && !acc_out && !getenv("YB_TC_NO_TMA_EPI") && !getenv("YB_TC_NO_COALESCE")) p.tma_epi = 32;
+    // alternate tiles per group: -24 % on 32->64 3x3 @304, -17 % on the BN = 64 1x1 layers, but +5 % on BN = 128 (measured);
+    // BN = 32 tiles have a single 32-column slab, so alternating is the only way to use both groups at all
+    p.epi_alt = ((BN == 32 && (kind == 0 || i8kind)) || (p.tma_epi && (BN <= 64 || getenv("YB_TC_EPI_ALT_128")) && BN <= 128)) &&
+                !getenv("YB_TC_NO_EPI_ALT") ? 1 : 0;
     const size_t ring_budget = (size_t)(p.tma_epi == 64 ? 158 : 191) * 1024;   // what is left of 227 KB beside the epilogue tiles
     bool use_halo = false;
-    if (l.size == 3 && l.stride == 1 && l.pad == 1 && !no_halo && !getenv("YB_TC_NO_HALO") && (kind == 0 || getenv("YB_TC_HALO_ALL"))) {
+    if (l.size == 3 && l.stride == 1 && l.pad == 1 && !no_halo && !getenv("YB_TC_NO_HALO") && (kind == 0 || ((kind == 1 || kind == 2) && !getenv("YB_TC_I8_NO_HALO")))) {
         const double t_halo = layout(true), t_tap = layout(false);
         use_halo = t_halo < 0.97 * t_tap || getenv("YB_TC_HALO") != nullptr;
     }
@@ -1559,7 +1633,7 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
     // UMMA instruction descriptor (kind::f16): D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TC_BM * p.cg) >> 4) << 24);
     // kind::i8: D = s32 (2 at bit 4), A = B = signed 8 bit (1 at bits 7 / 10)
-    if (i8) p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    if (i8) p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TC_BM * p.cg) >> 4) << 24);
     // kind::tf32: D = f32, A = B = tf32 (format 2): the tensor core reads the f32 words in place
     if (kind == 3) p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     // smem descriptor high word: SBO (8 rows * row bytes) >> 4 at bits 32..45, version 1 at bit 46, swizzle at 61..63
@@ -1619,19 +1693,21 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
     }
     plan->tmO = plan->tmA; plan->tmR = plan->tmA;   // valid placeholders when the TMA epilogue is off
     if (p.tma_epi) {
+        const int oesz = out_bf16 ? 2 : 4;
         auto encode_px = [&](CUtensorMap *tm, const TV &t, const char *what) {
-            // (channels, padded x, merged padded rows) of a bf16 padded-NHWC tensor; box = one 64-channel slab of a pixel tile
+            // (channels, padded x, merged padded rows) of a padded-NHWC tensor (bf16, or f32 for the integer kinds); box = one
+            // slab of a pixel tile
             cuuint64_t dims[3] = {(cuuint64_t)l.n, (cuuint64_t)t.Wp, (cuuint64_t)t.N * t.Hp};
-            cuuint64_t strides[2] = {(cuuint64_t)t.ldc * 2, (cuuint64_t)t.Wp * t.ldc * 2};
+            cuuint64_t strides[2] = {(cuuint64_t)t.ldc * oesz, (cuuint64_t)t.Wp * t.ldc * oesz};
             cuuint32_t box[3] = {(cuuint32_t)p.tma_epi, (cuuint32_t)p.TW, (cuuint32_t)p.TH};
             cuuint32_t es[3] = {1, 1, 1};
-            CUresult rr = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, t.base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              p.tma_epi == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            CUresult rr = enc(tm, out_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, t.base, dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, p.tma_epi * oesz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (rr != CUDA_SUCCESS) { delete plan; fatal_throw(std::string("cuTensorMapEncodeTiled(") + what + ") failed: " + std::to_string((int)rr)); }
         };
         encode_px(&plan->tmO, out, "output");
-        if (res.base) encode_px(&plan->tmR, res, "residual");
+        if (res.base && out_bf16) encode_px(&plan->tmR, res, "residual");
     }
     plan->pdl = (getenv("YB_NO_PDL") == nullptr) ? 1 : 0;
     plan->grid = (p.cg == 2) ? 2 * std::min(p.num_work, sms / 2) : std::min(p.num_tiles, sms);
@@ -1645,13 +1721,19 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
                  (p.tma_epi ? 1024 + 4 * (size_t)(128 * p.tma_epi * 2) /*TMA epilogue: [OUT | RES] tile per warp group*/
                             : 128 + 4096 * TC_EPI_WARPS /*epilogue staging*/);
     if (plan->smem > 227 * 1024) { delete plan; fatal_throw("tc plan: shared memory budget exceeded"); }
-    if (cudaFuncSetAttribute(k_conv_tc<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(k_conv_tc<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(k_conv_tc<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(k_conv_tc<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(k_conv_tc<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(k_conv_tc<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-        fatal_throw("cudaFuncSetAttribute(k_conv_tc) failed");
+    {
+        const void *fns[] = {(const void *)k_conv_tc<1, false, false, 0>, (const void *)k_conv_tc<2, false, false, 0>,
+                             (const void *)k_conv_tc<1, false, false, 1>, (const void *)k_conv_tc<2, false, false, 1>,
+                             (const void *)k_conv_tc<1, false, false, 2>, (const void *)k_conv_tc<2, false, false, 2>,
+                             (const void *)k_conv_tc<2, false, true, 2>,
+                             (const void *)k_conv_tc<1, true, false, 0>, (const void *)k_conv_tc<2, true, false, 0>,
+                             (const void *)k_conv_tc<1, false, true, 0>, (const void *)k_conv_tc<2, false, true, 0>,
+                             (const void *)k_conv_tc<1, false, true, 1>, (const void *)k_conv_tc<2, false, true, 1>,
+                             (const void *)k_conv_tc<1, false, true, 2>};
+        for (const void *f : fns)
+            if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+                fatal_throw("cudaFuncSetAttribute(k_conv_tc) failed");
+    }
     return plan;
 }
 
@@ -1807,15 +1889,21 @@ void tc_launch(void *vp, cudaStream_t s) {
     static const bool ks_always = getenv("YB_TC_KS_ALWAYS") != nullptr;   // experiment: one kernel variant for every layer
     const bool ks = plan->p.sk_T > 0 || ks_always;
     const bool st = plan->p.stats != nullptr && !ks;   // role counters: a separate instantiation (YB_TC_STATS=1)
+    const int epi = (plan->p.kind == 1 || plan->p.kind == 2) ? 2 : plan->p.tma_epi ? 1 : 0;
+    const TcPlan &P = *plan;
+#define YB_TC_LAUNCH(CG_, KS_, ST_, EPI_) cudaLaunchKernelEx(&cfg, k_conv_tc<CG_, KS_, ST_, EPI_>, P.tmA, P.tmB, P.tmO, P.tmR, P.p)
     if (plan->p.cg == 2) {
-        if (ks) cudaLaunchKernelEx(&cfg, k_conv_tc<2, true, false>, plan->tmA, plan->tmB, plan->tmO, plan->tmR, plan->p);
-        else if (st) cudaLaunchKernelEx(&cfg, k_conv_tc<2, false, true>, plan->tmA, plan->tmB, plan->tmO, plan->tmR, plan->p);
-        else cudaLaunchKernelEx(&cfg, k_conv_tc<2, false, false>, plan->tmA, plan->tmB, plan->tmO, plan->tmR, plan->p);
+        if (ks) YB_TC_LAUNCH(2, true, false, 0);
+        else if (epi == 1) { if (st) YB_TC_LAUNCH(2, false, true, 1); else YB_TC_LAUNCH(2, false, false, 1); }
+        else if (epi == 2) { if (st) YB_TC_LAUNCH(2, false, true, 2); else YB_TC_LAUNCH(2, false, false, 2); }
+        else { if (st) YB_TC_LAUNCH(2, false, true, 0); else YB_TC_LAUNCH(2, false, false, 0); }
     } else {
-        if (ks) cudaLaunchKernelEx(&cfg, k_conv_tc<1, true, false>, plan->tmA, plan->tmB, plan->tmO, plan->tmR, plan->p);
-        else if (st) cudaLaunchKernelEx(&cfg, k_conv_tc<1, false, true>, plan->tmA, plan->tmB, plan->tmO, plan->tmR, plan->p);
-        else cudaLaunchKernelEx(&cfg, k_conv_tc<1, false, false>, plan->tmA, plan->tmB, plan->tmO, plan->tmR, plan->p);
+        if (ks) YB_TC_LAUNCH(1, true, false, 0);
+        else if (epi == 1) { if (st) YB_TC_LAUNCH(1, false, true, 1); else YB_TC_LAUNCH(1, false, false, 1); }
+        else if (epi == 2) { if (st) YB_TC_LAUNCH(1, false, true, 2); else YB_TC_LAUNCH(1, false, false, 2); }
+        else { if (st) YB_TC_LAUNCH(1, false, true, 0); else YB_TC_LAUNCH(1, false, false, 0); }
     }
+#undef YB_TC_LAUNCH
 }
 
 void tc_free_plan(void *vp) {

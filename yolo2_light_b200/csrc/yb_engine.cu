@@ -537,7 +537,7 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
 
     // ---- op list -----------------------------------------------------------------------------------
     Engine *E = e.get();
-    bool stem_fused = false;
+    bool stem_fused = false, stem_pool_fused = false;
     {
         // ops[0] consumes the caller's NCHW f32 images.  Usually that is the stem convolution itself (3 input
         // channels, 3x3/1/1), reading NCHW directly; otherwise a plain NCHW -> padded-NHWC conversion.
@@ -546,7 +546,39 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                              l0.size == 3 && l0.stride == 1 && l0.pad == 1 && (l0.n == 16 || l0.n == 32) &&
                              fused_into[0] < 0 && e->out_tv[0].base && !getenv("YB_NO_STEM") &&
                              (e->out_dt[0] == DT_F32 || (e->out_tv[0].ldc % 8 == 0));
-        if (stem_ok && stem_w_off != (size_t)-1 && e->out_dt[0] == DT_BF16 && tc_stem_supported(l0, e->out_tv[0]) &&
+        // exact nets: stem + 2x2/2 max-pool + the integer layer's input conversion in one kernel (k_stem_pool): layers 0 and 1
+        // are then never written to HBM
+        bool pool_ok = stem_ok && opt.fuse && e->out_dt[0] == DT_F32 && l0.n == 16 && nl > 2 && !getenv("YB_NO_STEM_POOL_FUSE");
+        if (pool_ok) {
+            const Layer &mp = net->layers[1], &c2 = net->layers[2];
+            pool_ok = mp.type == YB_MAXPOOL && mp.size == 2 && mp.stride == 2 && mp.pad == 1 && cons[0].size() == 1 && cons[0][0] == 1 &&
+                      cons[1].size() == 1 && cons[1][0] == 2 && c2.type == YB_CONVOLUTIONAL && conv_variant(2) != 0 &&
+                      side_off[2] != (size_t)-1 && !xnor_fallback(c2) && !(conv_variant(2) == 1 && xnor_on_tc(c2)) &&
+                      (conv_variant(2) == 1 || side_ld[2] % 16 == 0);
+        }
+        if (pool_ok) {
+            stem_fused = true; stem_pool_fused = true;
+            const Layer &c2 = net->layers[2];
+            const int v2 = conv_variant(2);
+            const TV q = (v2 == 2) ? make_tv(e->act_arena + side_off[2], B, c2.h, c2.w, c2.c, side_ld[2], P, DT_S8, 0)
+                                   : make_tv(e->act_arena + side_off[2], B, c2.h, c2.w, side_ld[2], side_ld[2], P, DT_BITS, 0);
+            StemW<16> w16{};
+            for (int f = 0; f < 16; ++f) {
+                for (int c = 0; c < 3; ++c)
+                    for (int t = 0; t < 9; ++t) w16.w[(t * 3 + c) * 16 + f] = l0.weights[((size_t)f * 3 + c) * 9 + t];
+                w16.b[f] = l0.biases[f];
+            }
+            const int act = l0.activation, H = l0.h, W = l0.w;
+            const float mult = (v2 == 2) ? c2.input_quant_multipler : 0.f;
+            const int grid = (int)(((long)B * c2.h * c2.w + 127) / 128);
+            prefilled[2] = 1;
+            e->not_materialised[0] = e->not_materialised[1] = 1;
+            e->first_kind = OP_CONV_SIMT; e->first_layer = 0;
+            e->first_op = [=](const float *din, cudaStream_t s) {
+                if (v2 == 2) k_stem_pool<0><<<grid, 128, 0, s>>>(din, q, w16, act, H, W, mult);
+                else k_stem_pool<2><<<grid, 128, 0, s>>>(din, q, w16, act, H, W, mult);
+            };
+        } else if (stem_ok && stem_w_off != (size_t)-1 && e->out_dt[0] == DT_BF16 && tc_stem_supported(l0, e->out_tv[0]) &&
             !getenv("YB_NO_STEM_TC")) {
             // tensor-core stem: gathers the 3x3x3 window from NCHW, K padded 27 -> 32
             stem_fused = true;
@@ -598,6 +630,7 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
             if (!prev_ok) fatal_throw("engine: layer " + std::to_string(i) + " has no image input");
         };
         if (i == 0 && stem_fused) continue;
+        if (i == 1 && stem_pool_fused) continue;
         switch (l.type) {
         case YB_CONVOLUTIONAL: {
             need_prev();

@@ -832,6 +832,85 @@ __global__ void k_maxpool_fused(TV in /* f32 */, TV q, int size, int stride, int
 }
 
 // upsample_cpu forward (reference yolov2_forward_network.c:380-394): out = scale * in[y/stride][x/stride]
+// ------------------------------------------------------------------------------------------------------
+// Exact nets (INT8 / XNOR tiny models): stem convolution + 2x2/2 max-pool + the next integer layer's input conversion in ONE
+// kernel.  Layers 0-2 of yolov3-tiny / tiny-yolo-obj_xnor are conv 3->16 (f32), maxpool 2/2, integer conv: unfused, the f32 stem
+// output (709 MB at 416x416 batch 64) is written once and read once just to be reduced 4:1 and narrowed to one byte (or bit)
+// per value.  One thread per POOLED pixel: the 4x4x3 input window (48 loads), four stem outputs x 16 filters in the
+// reference's exact order (c, ky, kx; separately rounded products and sums: k_conv_stem<EXACT>), bias + activation, the
+// reference's max (forward_maxpool_layer_avx scalar semantics: -FLT_MAX start, strict >), then quant_i8 / sign exactly as
+// k_maxpool_fused.  Bit-identical to the three separate kernels.
+// MODE 0: s8 quantised (q.ldc bytes per pixel, channels >= 16 stay zero); 2: sign bits (one word per pixel).
+// ------------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(128) k_stem_pool(const float *__restrict__ in, TV q, const __grid_constant__ StemW<16> sw, int act,
+                                                   int H, int W, float mult) {
+    constexpr int NF = 16;
+    const int OH = q.H, OW = q.W;
+    const long total = (long)q.N * OH * OW;
+    const long pidx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (pidx >= total) return;
+    const int px = (int)(pidx % OW), py = (int)((pidx / OW) % OH), n = (int)(pidx / ((long)OW * OH));
+    const float *img = in + (size_t)n * 3 * H * W;
+    float acc[4][NF];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int f = 0; f < NF; ++f) acc[k][f] = 0.f;
+    const int y0 = 2 * py - 1, x0 = 2 * px - 1;            // top-left of the 4x4 input window
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float win[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int iy = y0 + a, ix = x0 + b;
+                win[a][b] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(img + ((size_t)c * H + iy) * W + ix) : 0.f;
+            }
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    const float wv = sw.w[((ky * 3 + kx) * 3 + c) * NF + f];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)     // output pixel (dy, dx) = (k >> 1, k & 1)
+                        acc[k][f] = __fadd_rn(acc[k][f], __fmul_rn(wv, win[(k >> 1) + ky][(k & 1) + kx]));
+                }
+    }
+    float m[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        float mx = -3.402823466e+38f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                       // window order of the reference: rows, then columns
+            const bool inside = (2 * py + (k >> 1)) < H && (2 * px + (k & 1)) < W;
+            const float v = act_exact(__fadd_rn(acc[k][f], sw.b[f]), act);
+            if (inside) mx = v > mx ? v : mx;
+        }
+        m[f] = mx;
+    }
+    if (MODE == 0) {
+        uint32_t wq[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            uint32_t word = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) word |= (uint32_t)(quant_i8(m[g * 4 + j], mult) & 0xff) << (8 * j);
+            wq[g] = word;
+        }
+        *reinterpret_cast<uint4 *>(tv_px<int8_t>(q, n, py, px)) = make_uint4(wq[0], wq[1], wq[2], wq[3]);
+    } else {
+        uint32_t word = 0;
+#pragma unroll
+        for (int j = 0; j < NF; ++j)
+            if (m[j] > 0.f) word |= 1u << j;
+        tv_px<uint32_t>(q, n, py, px)[0] = word;
+    }
+}
+
 template <typename T>
 __global__ void k_upsample(TV in, TV out, int stride, float scale) {
     const long total = (long)out.N * out.H * out.W * out.C;
