@@ -449,5 +449,13 @@ def test_fused_stem_pool_is_bit_identical_to_the_three_kernels(builder, w, h, q,
         b.fetch_layer(0, quantized=bool(q))
     assert np.array_equal(a.fetch_counts(2, quantized=bool(q)), b.fetch_counts(2, quantized=bool(q)))
     assert util.bits_equal(a.fetch_layer(2, quantized=bool(q)), b.fetch_layer(2, quantized=bool(q)))
+    # every later integer layer sees identical inputs: raw accumulators / popcounts equal to the end of the trunk
+    n_int = 0
+    for i, l in enumerate(a.layers):
+        if l["type_name"] == "CONVOLUTIONAL" and i >= 2 and (l["xnor"] or (q and l["activation"] != 3)):
+            assert np.array_equal(a.fetch_counts(i, quantized=bool(q)), b.fetch_counts(i, quantized=bool(q))), i
+            n_int += 1
+    assert n_int >= 6
+    # the detection tensors differ only by the head's fused [yolo] epilogue (fast logistic) that `fuse` also switches on
     for i, o in a.detection_outputs().items():
-        assert util.bits_equal(o, b.layer_output(i)), (builder.__name__, i)
+        assert util.rel_l2(o, b.layer_output(i)) <= 1e-5, (builder.__name__, i)

@@ -147,10 +147,10 @@ static __global__ void __launch_bounds__(128) k_det_iou(DetParams P, const float
     const int b = blockIdx.z;
     const int n = min(counts[b], P.max_rows);
     const int words = (P.max_rows + 31) / 32;
-    const int i = blockIdx.y;
     const int wd = blockIdx.x * 128 + threadIdx.x;
-    if (i >= n || wd >= words || wd * 32 >= n) return;
+    if (wd >= words || wd * 32 >= n) return;
     const int stride = 5 + P.classes;
+    for (int i = blockIdx.y; i < n; i += gridDim.y) {        // grid.y is capped: the pipelined path sizes it without knowing n
     const float *ri = rows + ((size_t)b * P.max_rows + i) * stride;
     const float ax = ri[0], ay = ri[1], aw = ri[2], ah = ri[3];
     unsigned m = 0;
@@ -165,6 +165,7 @@ static __global__ void __launch_bounds__(128) k_det_iou(DetParams P, const float
         if (__fdiv_rn(inter, uni) > P.nms) m |= 1u << j;
     }
     mask[((size_t)b * P.max_rows + i) * words + wd] = m;
+    }
 }
 
 // one block per (class, image); dynamic smem: keys float[P2], idx int[P2], alive unsigned[words]

@@ -1320,7 +1320,7 @@ static void det_launch_count_emit(const DetParams &P, Engine::DetWs &ws, int B, 
 static void det_launch_nms(const DetParams &P, Engine::DetWs &ws, int B, int nmax, cudaStream_t s) {
     if (!(P.nms > 0.f) || nmax <= 0) return;
     const int capw = (ws.cap + 31) / 32;
-    k_det_iou<<<dim3((unsigned)((capw + 127) / 128), (unsigned)nmax, (unsigned)B), 128, 0, s>>>(P, ws.rows, ws.counts, ws.mask);
+    k_det_iou<<<dim3((unsigned)((capw + 127) / 128), (unsigned)std::min(nmax, 256), (unsigned)B), 128, 0, s>>>(P, ws.rows, ws.counts, ws.mask);
     int P2 = 1; while (P2 < nmax) P2 <<= 1;
     const size_t smem = (size_t)P2 * 8 + (size_t)capw * 4;
     if (smem > 48 * 1024)
@@ -1392,15 +1392,21 @@ int engine_submit_u8(Engine *e, Network *net, const unsigned char *host_u8, int 
     CUDA_OK(cudaEventRecord(sl.ev_in, e->s_in));
     CUDA_OK(cudaStreamWaitEvent(e->stream, sl.ev_in, 0));
     engine_forward(e, sl.d_in, e->stream);
-    // earlier readers of d_out[k] (decode / D2H of the ticket that used this slot before) must be done
-    CUDA_OK(cudaStreamWaitEvent(e->stream, sl.ev_det, 0));
-    CUDA_OK(cudaStreamWaitEvent(e->stream, sl.ev_done, 0));
-    for (size_t i = 0; i < e->d_final.size(); ++i)
-        if (e->d_final[i] && (net->layers[i].type == YB_YOLO || net->layers[i].type == YB_REGION))
-            CUDA_OK(cudaMemcpyAsync(sl.d_out[i], e->d_final[i], e->final_count[i] * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+    // Candidate selection + box decode (k_det_count / k_det_emit: they read the objectness planes and, for the few candidates,
+    // their class scores) run right behind the forward on the compute stream, straight on the engine's yolo tensors -- the next
+    // forward overwrites those, so this is the only part that must not slip.  What follows (IoU matrix + per-class NMS) works on
+    // the slot's own candidate rows and goes to the side stream, where it overlaps the next batch's forward.  (Copying the
+    // 124 MB of yolo tensors into the slot first, as the raw-tensor path does, cost more than the decode itself.)
+    CUDA_OK(cudaStreamWaitEvent(e->stream, sl.ev_det, 0));     // the slot's previous NMS / counts copy are done with its workspace
+    DetParams P1 = P0;
+    {
+        int k2 = 0;
+        for (size_t i = 0; i < net->layers.size(); ++i)
+            if (net->layers[i].type == YB_YOLO || net->layers[i].type == YB_REGION) P1.L[k2++].p = e->d_final[i];
+    }
+    det_launch_count_emit(P1, sl.det, B, e->stream);
     CUDA_OK(cudaEventRecord(sl.ev_comp, e->stream));
     CUDA_OK(cudaStreamWaitEvent(e->s_det, sl.ev_comp, 0));
-    det_launch_count_emit(P0, sl.det, B, e->s_det);
     CUDA_OK(cudaMemcpyAsync(sl.h_counts, sl.det.counts, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, e->s_det));
     det_launch_nms(P0, sl.det, B, max_rows, e->s_det);   // no host round trip: grids sized for the cap, kernels read the counts
     CUDA_OK(cudaEventRecord(sl.ev_det, e->s_det));
