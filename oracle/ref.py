@@ -113,6 +113,14 @@ class RefNet:
             return a.reshape(L["batch"], L["out_c"], L["out_h"], L["out_w"])
         return a.reshape(L["batch"], -1)
 
+    def set_output(self, i: int, a: np.ndarray) -> None:
+        """Plant an activation in the reference layer's host l.output (what ROUTE / SHORTCUT layers read from their sources)."""
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        L = self.layers[i]
+        assert a.size == L["outputs"] * L["batch"], (a.shape, L["outputs"], L["batch"])
+        p = self.lib.refh_layer_ptr(self.h, i, b"output")
+        C.memmove(p, a.ctypes.data, a.nbytes)
+
     def predict(self, x: np.ndarray) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=np.float32)
         assert x.size == self.inputs * self.batch, (x.shape, self.inputs, self.batch)

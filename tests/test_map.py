@@ -159,3 +159,33 @@ def test_map_driver_loop_equals_reference_end_to_end(workdir):
     tp, fp, fn = re.search(r"TP = (\d+), FP = (\d+), FN = (\d+)", out).groups()
     assert abs(mAP - map_ref) < 5e-7
     assert (int(st["tp"]), int(st["fp"]), int(st["fn"])) == (int(tp), int(fp), int(fn))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_map_driver_on_the_gpu_equals_validate_detector_map(precision, workdir):
+    """SURVEY 8f row 4 on the device: dataset.evaluate_map with the REAL Network -- u8 frames -> yb_network_predict_image_u8
+    (device resize) -> forward -> yb_network_detect (device decode + NMS) -> yb_map_evaluate -- on the on-disk dataset the
+    reference's validate_detector_map (src/additionally.c:4541-4898) was run on: same TP / FP / FN, same mAP."""
+    import yolo2_light_b200 as yb
+    from yolo2_light_b200 import dataset
+    name = "tiny64"
+    cfg, wts = util.model_files(name, workdir)
+    root = os.path.join(workdir, "mapset_tiny64_50")          # written by test_map_accounting_equals_reference
+    if not os.path.exists(os.path.join(root, "ref_stdout.txt")):
+        test_map_accounting_equals_reference(name, 0.5, workdir)
+    paths, names, truth = dataset.load_validation_set(os.path.join(root, "data.cfg"))
+    net = yb.load_network(cfg, wts, batch=2)                  # 7 images: exercises the padded last batch
+    if precision == "fp32":
+        net.set_precision(yb.YB_PREC_FP32)
+    classes = len(names)
+    mAP, aps, st = dataset.evaluate_map(net, paths, truth, classes, 0.5, 0.24)
+    out = open(os.path.join(root, "ref_stdout.txt")).read()
+    map_ref = float(re.search(r"mean average precision \(mAP\) = ([0-9.]+)", out).group(1))
+    tp, fp, fn = (int(v) for v in re.search(r"TP = (\d+), FP = (\d+), FN = (\d+)", out).groups())
+    if precision == "fp32":
+        assert abs(mAP - map_ref) < 5e-6
+        assert (int(st["tp"]), int(st["fp"]), int(st["fn"])) == (tp, fp, fn)
+    else:   # bf16 tensor cores: detections within 1e-3 of the reference's; a borderline box may change sides
+        assert abs(mAP - map_ref) < 0.02
+        assert abs(int(st["tp"]) - tp) <= 2 and abs(int(st["fn"]) - fn) <= 2
