@@ -475,13 +475,24 @@ def main():
             tsum = sum(t for _, t in by[dom]) * 1e-3
             ach = fl / tsum / 1e12
             peak = peaks.get("bf16_tflops_sustained", 1400.0)
+            unit = "TFLOP/s"
+            if dom in ("conv_tc_i8", "conv_int8"):
+                # integer workloads: the denominator is the kind::i8 MMA rate measured on this pool (SURVEY 8d asks for it;
+                # MEASURED_PEAKS.json only has bf16), scaled by what a real cuBLAS GEMM reaches of the bf16 MMA-only rate
+                try:
+                    ip = json.load(open(os.path.join(ROOT, "profiles", "r02_int8_peak.json")))
+                    peak = ip["int8_tops_mma_only"] * peaks.get("bf16_tflops_sustained", 1393.7) / ip["bf16_tflops_mma_only"]
+                    src = "kind::i8 MMA-only probe (profiles/r02_int8_peak.json) x cuBLAS-to-MMA-only bf16 ratio"
+                    unit = "TOP/s"
+                except Exception:
+                    pass
             kname = {"conv_tc2": "k_conv_tc<2> (tcgen05 cta_group::2 implicit-GEMM conv)",
                      "conv_tc": "k_conv_tc<1> (tcgen05 implicit-GEMM conv)"}.get(dom, dom)
-            all_tc = [(li, t) for k in ("conv_tc", "conv_tc2") for li, t in by.get(k, [])]
+            all_tc = [(li, t) for k in ("conv_tc", "conv_tc2", "conv_tc_i8", "conv_tc_tf32") for li, t in by.get(k, [])]
             fl_all = sum(2 * shapes[li]["n"] * shapes[li]["size"] ** 2 * shapes[li]["c"] * shapes[li]["out_h"] *
                          shapes[li]["out_w"] * batch for li, _ in all_tc)
             t_all = sum(t for _, t in all_tc) * 1e-3
-            roof = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+            roof = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak, "unit": unit,
                     "all_tensor_core_convs": {"achieved": fl_all / max(t_all, 1e-12) / 1e12, "launches": len(all_tc),
                                               "frac": fl_all / max(t_all, 1e-12) / 1e12 / peak,
                                               "share_of_step": t_all * 1e3 / sum(t for _, _, t in prof)},

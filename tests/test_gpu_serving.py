@@ -28,18 +28,20 @@ def _net(builder, slim, w, h, workdir, tag, batch, q=0, seed=51):
     return yb.load_network(cfg, wts, batch=batch, quantized=q), cfg, wts
 
 
-@pytest.mark.parametrize("builder,slim,q,thresh", [(cfgs.yolov3_tiny, 2, 0, 0.3), (cfgs.yolov3, 4, 0, 0.3), (cfgs.yolov3_tiny, 2, 1, 0.3),
-                                                  (cfgs.tiny_yolo_obj_xnor, 2, 0, 0.05)])
-def test_pipelined_u8_detections_equal_sync_calls(builder, slim, q, thresh, workdir):
+@pytest.mark.parametrize("builder,slim,q,thresh,fw,fh", [(cfgs.yolov3_tiny, 2, 0, 0.3, 120, 96), (cfgs.yolov3, 4, 0, 0.3, 120, 96),
+                                                        (cfgs.yolov3_tiny, 2, 1, 0.3, 120, 96), (cfgs.tiny_yolo_obj_xnor, 2, 0, 0.05, 120, 96),
+                                                        # frames of exactly the network size: the stem reads the 8-bit frames itself
+                                                        (cfgs.yolov3, 4, 0, 0.3, 160, 128), (cfgs.yolov3_tiny, 2, 0, 0.3, 160, 128)])
+def test_pipelined_u8_detections_equal_sync_calls(builder, slim, q, thresh, fw, fh, workdir):
     B, W, H = 3, 160, 128
     net, _, _ = _net(builder, slim, W, H, workdir, f"{builder.__name__}_{q}", B, q)
     rng = np.random.default_rng(5)
-    frames = [rng.integers(0, 256, size=(B, 96, 120, 3), dtype=np.uint8) for _ in range(5)]   # resized 120x96 -> 160x128 on the device
+    frames = [rng.integers(0, 256, size=(B, fh, fw, 3), dtype=np.uint8) for _ in range(5)]   # 120x96 frames are resized on the device
     # expected: the synchronous pair predict_image_u8 + detect, frame set by frame set
     exp = []
     for f in frames:
         net.predict_image_u8(f, quantized=bool(q))
-        dets, counts = net.detect(120, 96, thresh, 0.45, max_rows=2048, quantized=bool(q))
+        dets, counts = net.detect(fw, fh, thresh, 0.45, max_rows=2048, quantized=bool(q))
         exp.append(([d.copy() for d in dets], counts.copy()))
     assert sum(int(c.sum()) for _, c in exp) > 20
     inflight, got, moved = [], [], 0

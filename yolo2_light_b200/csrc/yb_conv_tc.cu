@@ -1306,6 +1306,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 // ------------------------------------------------------------------------------------------------------
 struct StemTcP {
     const float *in;          // NCHW f32, set per call
+    const unsigned char *in8; // or: HWC 8-bit frames of exactly the network size (k_stem_tc<true>), set per call
     char *out; int out_ldc;   // bf16 padded NHWC
     const __nv_bfloat16 *w;   // [32 rows (filters, zero padded)][32 k] bf16, k = (ky,kx,c), k >= 27 zero
     const float *bias;
@@ -1314,6 +1315,10 @@ struct StemTcP {
     int ntiles;
 };
 
+// U8: the input is the caller's 8-bit HWC frame (already of the network size): value = (float)((double)v / 255.0) exactly as
+// load_image_stb computes it (additionally.c:3093-3103), through a 256-entry table -- the u8 -> planar float pass over the batch
+// (71 MB written, 71 MB read back) disappears from the serving path.
+template <bool U8>
 __global__ void __launch_bounds__(128) k_stem_tc(StemTcP p) {
     __shared__ __align__(1024) uint8_t a_tile[128 * 64];
     __shared__ __align__(1024) uint8_t b_tile[32 * 64];
@@ -1321,7 +1326,9 @@ __global__ void __launch_bounds__(128) k_stem_tc(StemTcP p) {
     __shared__ uint32_t tmem_slot;
     __shared__ float bias_s[32];
     __shared__ unsigned long long optr[128];   // global address of every pixel's output row of the current tile (0: none)
+    __shared__ float lut[U8 ? 256 : 1];
     const int t = threadIdx.x, warp = t >> 5;
+    if constexpr (U8) { lut[t] = (float)((double)(float)t / 255.0); lut[t + 128] = (float)((double)(float)(t + 128) / 255.0); }
     const uint32_t a_addr = smem_u32(a_tile), b_addr = smem_u32(b_tile), bar = smem_u32(&mma_bar);
     if (t < 32) bias_s[t] = (t < p.nf) ? p.bias[t] : 0.f;
     {   // weights -> swizzled B tile (row f, 16-byte chunk j at f*64 + ((j ^ ((f>>1)&3)) << 4))
@@ -1351,8 +1358,31 @@ __global__ void __launch_bounds__(128) k_stem_tc(StemTcP p) {
         // ---- gather 27 taps (k = (ky*3 + kx)*3 + c), pad to 32, as bf16
         uint32_t packed[16];
         {
-            const float *img = p.in + (size_t)n * 3 * plane;
             float v[32];
+            if constexpr (U8) {
+                const unsigned char *img8 = p.in8 + (size_t)n * 3 * plane;
+                if (ok && x >= 1 && x + 1 < p.W && y >= 1 && y + 1 < p.H) {
+                    const unsigned char *r1 = img8 + ((size_t)y * p.W + x) * 3, *r0 = r1 - (size_t)p.W * 3, *r2 = r1 + (size_t)p.W * 3;
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) {          // j = kx * 3 + c: nine consecutive bytes per image row
+                        v[0 * 9 + j] = lut[__ldg(r0 - 3 + j)];
+                        v[1 * 9 + j] = lut[__ldg(r1 - 3 + j)];
+                        v[2 * 9 + j] = lut[__ldg(r2 - 3 + j)];
+                    }
+                } else {
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const int iy = y + ky - 1, ix = x + kx - 1;
+                            const bool in_img = ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+#pragma unroll
+                            for (int c = 0; c < 3; ++c)
+                                v[(ky * 3 + kx) * 3 + c] = in_img ? lut[__ldg(img8 + ((size_t)iy * p.W + ix) * 3 + c)] : 0.f;
+                        }
+                }
+            } else {
+            const float *img = p.in + (size_t)n * 3 * plane;
             if (ok && x >= 1 && x + 1 < p.W && y >= 1 && y + 1 < p.H) {
                 // interior pixel (all but the image frame): nine row pointers, immediate offsets -1 / 0 / +1 -- the bounds-checked
                 // form below costs ~10 integer instructions per tap and made this kernel issue-bound (ncu: 627 instructions per
@@ -1376,6 +1406,7 @@ __global__ void __launch_bounds__(128) k_stem_tc(StemTcP p) {
                     for (int c = 0; c < 3; ++c)
                         v[(ky * 3 + kx) * 3 + c] = in_img ? __ldg(img + (size_t)c * plane + (size_t)iy * p.W + ix) : 0.f;
                 }
+            }
             }
 #pragma unroll
             for (int k = 27; k < 32; ++k) v[k] = 0.f;
@@ -1862,7 +1893,14 @@ void tc_stem_launch(void *vp, const float *d_in_nchw, cudaStream_t s) {
     StemPlan *sp = reinterpret_cast<StemPlan *>(vp);
     StemTcP p = sp->p;
     p.in = d_in_nchw;
-    k_stem_tc<<<sp->grid, 128, 0, s>>>(p);
+    k_stem_tc<false><<<sp->grid, 128, 0, s>>>(p);
+}
+// 8-bit HWC frames of exactly the network size (3 channels): no planar-float staging
+void tc_stem_launch_u8(void *vp, const unsigned char *d_in_hwc, cudaStream_t s) {
+    StemPlan *sp = reinterpret_cast<StemPlan *>(vp);
+    StemTcP p = sp->p;
+    p.in8 = d_in_hwc;
+    k_stem_tc<true><<<sp->grid, 128, 0, s>>>(p);
 }
 void tc_stem_free_plan(void *vp) { delete reinterpret_cast<StemPlan *>(vp); }
 

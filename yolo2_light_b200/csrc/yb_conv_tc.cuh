@@ -38,6 +38,7 @@ int tc_plan_enable_ksplit(void *plan, float *ws, unsigned *flags);
 int tc_stem_supported(const Layer &l, const TV &out);
 void *tc_stem_make_plan(const Layer &l, const TV &out, const void *d_w_32x32_bf16, const float *d_bias);
 void tc_stem_launch(void *plan, const float *d_in_nchw, cudaStream_t s);
+void tc_stem_launch_u8(void *plan, const unsigned char *d_in_hwc, cudaStream_t s);   // frames already of the network size
 void tc_stem_free_plan(void *plan);
 int tc_plan_cta_group(void *plan);   // 1 or 2 (k_conv_tc<2>, CTA pairs)
 void tc_launch(void *plan, cudaStream_t s);

@@ -71,8 +71,19 @@ static __global__ void __launch_bounds__(256) k_det_emit(DetParams P, const int 
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int li = 0, cell = 0, a = 0;
     const bool f = det_flag(P, b, blockIdx.x * 256 + threadIdx.x, li, cell, a);
-    int offset = 0;
-    for (int k = 0; k < (int)blockIdx.x; ++k) offset += blkcnt[b * P.nblk + k];
+    // candidates of the blocks before this one: summed by the whole block (a serial loop over up to 89 dependent global loads in
+    // every thread made this kernel ~20 us of pure latency on the compute stream)
+    __shared__ int s_off;
+    if (threadIdx.x == 0) s_off = 0;
+    __syncthreads();
+    {
+        int part = 0;
+        for (int k = threadIdx.x; k < (int)blockIdx.x; k += 256) part += blkcnt[b * P.nblk + k];
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0 && part) atomicAdd(&s_off, part);
+    }
+    __syncthreads();
+    const int offset = s_off;
     const unsigned bal = __ballot_sync(0xffffffffu, f);
     if (lane == 0) warp_tot[warp] = __popc(bal);
     __syncthreads();

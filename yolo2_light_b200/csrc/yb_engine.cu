@@ -80,6 +80,7 @@ struct Engine {
     int n_tc = 0, n_ksplit = 0;
     float *ksplit_ws = nullptr; unsigned *ksplit_flags = nullptr;   // partial sums / flags of the K-split tail (yb_conv_tc.cu)
     std::function<void(const float *, cudaStream_t)> first_op;   // consumes the caller's NCHW images (pointer varies per call)
+    std::function<void(const unsigned char *, cudaStream_t)> first_op_u8;   // same from 8-bit HWC frames of the network size (if set)
     int first_kind = OP_INPUT, first_layer = -1;
     void *stem_plan = nullptr;
     unsigned char *d_u8 = nullptr; size_t u8_bytes = 0;   // staging of the caller's u8 images (device-side input pipeline)
@@ -575,8 +576,8 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
             e->not_materialised[0] = e->not_materialised[1] = 1;
             e->first_kind = OP_CONV_SIMT; e->first_layer = 0;
             e->first_op = [=](const float *din, cudaStream_t s) {
-                if (v2 == 2) k_stem_pool<0><<<grid, 128, 0, s>>>(din, q, w16, act, H, W, mult);
-                else k_stem_pool<2><<<grid, 128, 0, s>>>(din, q, w16, act, H, W, mult);
+                if (v2 == 2) k_stem_pool<0><<<grid, 128, 0, s>>>(din, q, w16, act, H, W, mult, 0x8000000080000000ull);
+                else k_stem_pool<2><<<grid, 128, 0, s>>>(din, q, w16, act, H, W, mult, 0x8000000080000000ull);
             };
         } else if (stem_ok && stem_w_off != (size_t)-1 && e->out_dt[0] == DT_BF16 && tc_stem_supported(l0, e->out_tv[0]) &&
             !getenv("YB_NO_STEM_TC")) {
@@ -587,6 +588,7 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
             e->stem_plan = sp;
             e->first_kind = OP_CONV_TC; e->first_layer = 0;
             e->first_op = [sp](const float *din, cudaStream_t s) { tc_stem_launch(sp, din, s); };
+            if (!getenv("YB_NO_STEM_U8")) e->first_op_u8 = [sp](const unsigned char *d8, cudaStream_t s) { tc_stem_launch_u8(sp, d8, s); };
         } else if (stem_ok) {
             stem_fused = true;
             const TV tout = e->out_tv[0];
@@ -1001,6 +1003,8 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
 }
 
 static void launch_input(Engine *e, const float *d_in, cudaStream_t s) { e->first_op(d_in, s); }
+static void engine_forward_impl(Engine *e, const void *d_input, const unsigned char *d_u8_frames, void *stream);
+void engine_forward(Engine *e, const void *d_input, void *stream) { engine_forward_impl(e, d_input, nullptr, stream); }
 
 void engine_upload_input(Engine *e, const float *host_input, void *stream) {
     cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
@@ -1026,11 +1030,12 @@ void engine_upload_u8(Engine *e, const unsigned char *host_u8, int w, int h, int
 
 void *engine_stream(Engine *e) { return e->stream; }
 
-void engine_forward(Engine *e, const void *d_input, void *stream) {
+static void engine_forward_impl(Engine *e, const void *d_input, const unsigned char *d_u8_frames, void *stream) {
     cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
     CUDA_OK(cudaSetDevice(e->opt.device));   // thread identity may change per call (threading)
     const float *din = d_input ? reinterpret_cast<const float *>(d_input) : e->d_input;
-    launch_input(e, din, s);
+    if (d_u8_frames) e->first_op_u8(d_u8_frames, s);   // stem straight from the 8-bit frames
+    else launch_input(e, din, s);
     if (!e->graph_exec && !e->graph_failed && getenv("YB_NO_GRAPH")) e->graph_failed = true;   // profiling aid
     if (!e->graph_exec && !e->graph_failed) {
         // capture everything after the input conversion once
@@ -1387,11 +1392,14 @@ int engine_submit_u8(Engine *e, Network *net, const unsigned char *host_u8, int 
     // the previous forward that read d_in[k] must have finished before it is overwritten
     CUDA_OK(cudaStreamWaitEvent(e->s_in, sl.ev_comp, 0));
     CUDA_OK(cudaMemcpyAsync(sl.d_u8, host_u8, bytes, cudaMemcpyHostToDevice, e->s_in));
-    const long total = (long)B * net->c * net->h * net->w;
-    k_resize_u8_to_nchw<<<grid_for(total), 256, 0, e->s_in>>>(sl.d_u8, B, w, h, net->c, sl.d_in, net->w, net->h);
+    const bool direct = e->first_op_u8 && w == net->w && h == net->h && net->c == 3;   // frames of the network size: no staging
+    if (!direct) {
+        const long total = (long)B * net->c * net->h * net->w;
+        k_resize_u8_to_nchw<<<grid_for(total), 256, 0, e->s_in>>>(sl.d_u8, B, w, h, net->c, sl.d_in, net->w, net->h);
+    }
     CUDA_OK(cudaEventRecord(sl.ev_in, e->s_in));
     CUDA_OK(cudaStreamWaitEvent(e->stream, sl.ev_in, 0));
-    engine_forward(e, sl.d_in, e->stream);
+    engine_forward_impl(e, sl.d_in, direct ? sl.d_u8 : nullptr, e->stream);
     // Candidate selection + box decode (k_det_count / k_det_emit: they read the objectness planes and, for the few candidates,
     // their class scores) run right behind the forward on the compute stream, straight on the engine's yolo tensors -- the next
     // forward overwrites those, so this is the only part that must not slip.  What follows (IoU matrix + per-class NMS) works on

@@ -832,6 +832,29 @@ __global__ void k_maxpool_fused(TV in /* f32 */, TV q, int size, int stride, int
 }
 
 // upsample_cpu forward (reference yolov2_forward_network.c:380-394): out = scale * in[y/stride][x/stride]
+// Packed f32x2 arithmetic of sm_100 (two IEEE round-to-nearest operations per instruction, each lane rounded on its own --
+// exactly __fmul_rn / __fadd_rn twice): halves the instruction count of the exact-order float convolutions.
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+// The product is written as fma(a, b, nz) with nz = (-0, -0) handed in at RUN TIME: RN(a*b + (-0)) == RN(a*b) bit for bit (sign of
+// zero included), and ptxas cannot prove the addend away.  A plain mul.rn.f32x2 + add.rn.f32x2 pair -- and even fma(a, b, literal
+// -0) + add -- it contracts into ONE FFMA2 (single rounding), --fmad=false or not, which silently breaks bit-exactness with the
+// reference's separately rounded gemm_nn (found in the SASS, caught by test_fused_stem_pool_is_bit_identical...).
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b, unsigned long long nz) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(nz));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // Exact nets (INT8 / XNOR tiny models): stem convolution + 2x2/2 max-pool + the next integer layer's input conversion in ONE
 // kernel.  Layers 0-2 of yolov3-tiny / tiny-yolo-obj_xnor are conv 3->16 (f32), maxpool 2/2, integer conv: unfused, the f32 stem
@@ -844,7 +867,7 @@ __global__ void k_maxpool_fused(TV in /* f32 */, TV q, int size, int stride, int
 // ------------------------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(128) k_stem_pool(const float *__restrict__ in, TV q, const __grid_constant__ StemW<16> sw, int act,
-                                                   int H, int W, float mult) {
+                                                   int H, int W, float mult, unsigned long long negzero2 /* 0x8000000080000000 */) {
     constexpr int NF = 16;
     const int OH = q.H, OW = q.W;
     const long total = (long)q.N * OH * OW;
@@ -852,34 +875,41 @@ __global__ void __launch_bounds__(128) k_stem_pool(const float *__restrict__ in,
     if (pidx >= total) return;
     const int px = (int)(pidx % OW), py = (int)((pidx / OW) % OH), n = (int)(pidx / ((long)OW * OH));
     const float *img = in + (size_t)n * 3 * H * W;
-    float acc[4][NF];
+    unsigned long long acc2[4][NF / 2];          // (filter 2j, filter 2j + 1) pairs: mul.rn.f32x2 / add.rn.f32x2
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
-        for (int f = 0; f < NF; ++f) acc[k][f] = 0.f;
+        for (int j = 0; j < NF / 2; ++j) acc2[k][j] = 0ull;
     const int y0 = 2 * py - 1, x0 = 2 * px - 1;            // top-left of the 4x4 input window
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        float win[4][4];
+        unsigned long long win2[4][4];
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 const int iy = y0 + a, ix = x0 + b;
-                win[a][b] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(img + ((size_t)c * H + iy) * W + ix) : 0.f;
+                const float v = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(img + ((size_t)c * H + iy) * W + ix) : 0.f;
+                win2[a][b] = f2_pack(v, v);
             }
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-                for (int f = 0; f < NF; ++f) {
-                    const float wv = sw.w[((ky * 3 + kx) * 3 + c) * NF + f];
+                for (int j = 0; j < NF / 2; ++j) {
+                    const float *wp = &sw.w[((ky * 3 + kx) * 3 + c) * NF + 2 * j];
+                    const unsigned long long w2 = f2_pack(wp[0], wp[1]);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)     // output pixel (dy, dx) = (k >> 1, k & 1)
-                        acc[k][f] = __fadd_rn(acc[k][f], __fmul_rn(wv, win[(k >> 1) + ky][(k & 1) + kx]));
+                    for (int k = 0; k < 4; ++k)     // output pixel (dy, dx) = (k >> 1, k & 1); per accumulator the order is (c, ky, kx)
+                        acc2[k][j] = f2_add(acc2[k][j], f2_mul(w2, win2[(k >> 1) + ky][(k & 1) + kx], negzero2));
                 }
     }
+    float acc[4][NF];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < NF / 2; ++j) f2_unpack(acc2[k][j], acc[k][2 * j], acc[k][2 * j + 1]);
     float m[NF];
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
