@@ -459,3 +459,22 @@ def test_fused_stem_pool_is_bit_identical_to_the_three_kernels(builder, w, h, q,
     # the detection tensors differ only by the head's fused [yolo] epilogue (fast logistic) that `fuse` also switches on
     for i, o in a.detection_outputs().items():
         assert util.rel_l2(o, b.layer_output(i)) <= 1e-5, (builder.__name__, i)
+    # production configuration (no raw-accumulator dump): the max-pools behind the integer convolutions run in their epilogues
+    # (tc_plan_fuse_pool) -- every integer layer that is still materialised is bit-identical to the unfused plan
+    c = yb.load_network(cfg, wts, batch=B, quantized=q)
+    c.predict(x, quantized=bool(q))
+    assert c.last_launches() < b.last_launches()
+    n_cmp = n_gone = 0
+    for i, l in enumerate(a.layers):
+        if not (l["type_name"] == "CONVOLUTIONAL" and i >= 2 and (l["xnor"] or (q and l["activation"] != 3))):
+            continue
+        try:
+            got = c.fetch_layer(i, quantized=bool(q))
+        except yb.YbError:
+            n_gone += 1
+            continue
+        assert util.bits_equal(got, a.fetch_layer(i, quantized=bool(q))), i
+        n_cmp += 1
+    assert n_cmp >= 3 and n_gone >= 2, (n_cmp, n_gone)
+    for i, o in a.detection_outputs().items():
+        assert util.rel_l2(o, c.layer_output(i)) <= 1e-5, (builder.__name__, i)

@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <climits>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -89,6 +90,14 @@ struct TcParams {
     // BN columns) instead of half the columns of every tile -- two tiles are in the epilogue at once; the per-tile epilogue of the
     // small tiles is a latency chain (TMEM load -> math -> barrier -> store), not a throughput problem.
     int epi_alt;
+    // Fused 2x2 / stride-2 max-pool + input conversion of the NEXT integer layer (integer kinds, halo tiles of 8 x 16 pixels):
+    // the epilogue reduces every 2x2 window inside the warp (lane ^ 1 = x neighbour, lane ^ 8 = y neighbour), quantises (pool_mode
+    // 1: quant_i8 with pool_mult) or takes the sign (pool_mode 2: +-1 bytes) and writes bytes straight into the next layer's s8
+    // input: the f32 activation and the pooled f32 tensor never reach HBM.  jshift = 1 moves every tile down one merged row so
+    // that window rows (oy even, oy + 1) fall into the same tile (the padded layout puts oy = 0 on an odd merged row).
+    int pool_mode, jshift;
+    float pool_mult;
+    signed char *pool_out; long pool_ldc; int pool_Hp, pool_Wp;   // next layer's s8 input: padded NHWC, bytes
     int sps;                                  // K-blocks per pipeline stage (amortises the per-stage barrier round trip)
     int kbs;                                  // pipeline stages per work item = ceil(kblocks / sps)
     // K-split tail (wave quantisation): the last num_work % G work items ("tail") are cut along K into slices of sk_L
@@ -435,7 +444,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 auto next_A = [&]() {
                     if (cbA == cblocks) { if (!sched_next<false>(schA, wA, d0, d1)) return; cbA = 0; }
                     const int m = (CG == 2) ? 2 * (wA / nt) + (int)rank : wA / nt;
-                    const int x0 = (m % xt) * p.TW, J0 = (m / xt) * p.TH;
+                    const int x0 = (m % xt) * p.TW, J0 = (m / xt) * p.TH + p.jshift;
                     if constexpr (ST) { const long long c0 = clock64(); mbar_wait(emptyA_bar(sa), pha ^ 1u, 5); w_tma += clock64() - c0; }   // [7]: wait on the A ring
                     else mbar_wait(emptyA_bar(sa), pha ^ 1u, 5);
                     const uint32_t fb = fullA_bar(sa);
@@ -474,7 +483,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 const int n_idx = w % nt;
                 const int m = (CG == 2) ? 2 * (w / nt) + (int)rank : w / nt;
                 const int x0 = (m % xt) * p.TW;
-                const int J0 = (m / xt) * p.TH;
+                const int J0 = (m / xt) * p.TH + p.jshift;
                 const int n0 = n_idx * p.BN + (int)rank * (p.BN / CG);
                 const int kb_begin = seg0 * sps, kb_end = min(kblocks, seg1 * sps);
                 // channel block, tap x/y, K column of the weight matrix at the first K-block of the segment
@@ -712,7 +721,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const int n_idx = w % p.nt;
             const int m = (CG == 2) ? 2 * (w / p.nt) + (int)rank : w / p.nt;
             const int ox = (m % p.xt) * p.TW + tx;
-            const int J = (m / p.xt) * p.TH + ty;
+            const int J = (m / p.xt) * p.TH + p.jshift + ty;
             const int n0 = n_idx * p.BN;
             const int img = J / p.PR;
             const int oy = J - img * p.PR - p.row_off;
@@ -916,6 +925,55 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 __syncwarp();
             };
 
+            // ---- fused 2x2/2 max-pool + conversion to the next integer layer's input (TcParams::pool_mode).  Both epilogue functions
+            // are monotone non-decreasing in the s32 accumulator (truncating /32, clamp, x positive ALPHA1, + bias, leaky; resp.
+            // x mean >= 0, + bias, leaky), so max over the window commutes with them EXACTLY: the window maximum is taken on the raw
+            // accumulators and the float epilogue runs once per pooled value.  Window = lanes {l, l^1, l^8, l^9} (tile rows are 8
+            // pixels wide).  The reduction is a reduce-scatter: lane^1 halves the 32 columns, lane^8 halves them again, every lane
+            // ends up with the maxima of 8 columns of its window and finishes those -- a quarter of the float work per lane.
+            // Elements outside the image count as "skipped" (INT_MIN) like the reference's out-of-range taps (additionally.c:1448-1482).
+            auto pool_store_raw = [&](const uint32_t (&v)[32], int f0) {
+                const bool b0 = lane & 1, b3 = lane & 8;
+                int h16[16], h8[8];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int lo_ = valid ? (int)v[j] : INT_MIN, hi_ = valid ? (int)v[j + 16] : INT_MIN;
+                    const int keep = b0 ? hi_ : lo_, send = b0 ? lo_ : hi_;
+                    const int got = __shfl_xor_sync(0xffffffffu, send, 1);
+                    h16[j] = max(keep, got);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int keep = b3 ? h16[j + 8] : h16[j], send = b3 ? h16[j] : h16[j + 8];
+                    const int got = __shfl_xor_sync(0xffffffffu, send, 8);
+                    h8[j] = max(keep, got);
+                }
+                const int cbase = f0 + (b0 ? 16 : 0) + (b3 ? 8 : 0);     // this lane's 8 columns of the slab
+                uint32_t w0 = 0, w1 = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int f = n0 + cbase + j;
+                    float t;
+                    if (p.kind == 1) {
+                        int q16 = h8[j] / 32;
+                        q16 = q16 > 32767 ? 32767 : (q16 < -32767 ? -32767 : q16);
+                        t = __fadd_rn(__fmul_rn((float)q16, p.alpha1), bs[cbase + j]);
+                        t = (p.act == ACT_LEAKY) ? ((t > 0.f) ? t : __fdiv_rn(t, 10.f)) : t;
+                    } else {
+                        t = __fadd_rn(__fmul_rn((float)h8[j], (f < p.n) ? __ldg(p.mean + f) : 0.f), bs[cbase + j]);
+                        t = act_exact(t, p.act);
+                    }
+                    int b8 = (p.pool_mode == 1) ? quant_i8(t, p.pool_mult) : (t > 0.f ? 1 : -1);
+                    if (f >= p.n) b8 = 0;
+                    if (j < 4) w0 |= (uint32_t)(b8 & 0xff) << (8 * j); else w1 |= (uint32_t)(b8 & 0xff) << (8 * (j - 4));
+                }
+                const int oye = oy & ~1, oxe = ox & ~1;                  // the window's origin: the same pooled pixel in all four lanes
+                if (img < p.N && oye >= 0 && oye < p.OH && oxe < p.OW && !(p.dbg & 4)) {
+                    signed char *dst = p.pool_out + ((size_t)(img * p.pool_Hp + (oye >> 1) + 1) * p.pool_Wp + (oxe >> 1) + 1) * (size_t)p.pool_ldc + n0 + cbase;
+                    *reinterpret_cast<uint2 *>(dst) = make_uint2(w0, w1);
+                }
+            };
+
             // ---- TMA store of one 32-column f32 slab (integer kinds): the group's [128 pixels][32 floats] tile, 128-byte rows with
             // the 128B swizzle, written by one thread per row and stored by one cp.async.bulk.tensor
             auto tma_store_f32_slab = [&](const float (&y)[32], int f0) {
@@ -936,7 +994,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 named_bar_sync(1 + g, 128);
                 if (boss) {
-                    tma_store_3d(&tmO, out_tile, n0 + f0, (m % p.xt) * p.TW + 1, (m / p.xt) * p.TH);
+                    tma_store_3d(&tmO, out_tile, n0 + f0, (m % p.xt) * p.TW + 1, (m / p.xt) * p.TH + p.jshift);
                     tma_store_commit();
                 }
             };
@@ -953,7 +1011,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     const int g = half;
                     const uint32_t out_tile = stg_base + (uint32_t)g * (2u * tile_bytes), res_tile = out_tile + tile_bytes;
                     const bool boss = (q == 0) && (lane == 0);           // issues this group's TMA traffic
-                    const int x0 = (m % p.xt) * p.TW, J0 = (m / p.xt) * p.TH;
+                    const int x0 = (m % p.xt) * p.TW, J0 = (m / p.xt) * p.TH + p.jshift;
                     const uint32_t rsw = (NV == 2) ? (uint32_t)(r & 7) : (uint32_t)((r >> 1) & 3);
                     const uint32_t row_off = (uint32_t)r * rowb;
                     const bool has_res = p.res != nullptr;
@@ -963,7 +1021,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     auto request_res = [&](int w_, int f_) {
                         const int m_ = (CG == 2) ? 2 * (w_ / p.nt) + (int)rank : w_ / p.nt;
                         mbar_arrive_expect_tx(resfull_bar(g), tile_bytes);
-                        tma_load_3d(res_tile, &tmR, resfull_bar(g), (w_ % p.nt) * p.BN + f_, (m_ % p.xt) * p.TW + 1, (m_ / p.xt) * p.TH);
+                        tma_load_3d(res_tile, &tmR, resfull_bar(g), (w_ % p.nt) * p.BN + f_, (m_ % p.xt) * p.TW + 1, (m_ / p.xt) * p.TH + p.jshift);
                     };
                     if (has_res && boss && !res_requested) request_res(w, cbeg);   // very first slab of this group
                     res_requested = true;
@@ -1039,6 +1097,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     uint32_t v0[32];
                     tmem_ld32(taddr + (uint32_t)f0, v0);
                     tmem_ld_wait();
+                    if (p.pool_mode) { pool_store_raw(v0, f0); continue; }
                     float y[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
@@ -1075,6 +1134,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     uint32_t v0[32];
                     tmem_ld32(taddr + (uint32_t)f0, v0);
                     tmem_ld_wait();
+                    if (p.pool_mode) { pool_store_raw(v0, f0); continue; }
                     float y[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
@@ -1537,7 +1597,7 @@ int tc_conv_supported(const Layer &l, const TV &in, const TV &out, bool out_bf16
 
 static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &out, bool out_bf16, const TV &res,
                               bool res_bf16, int act2, const void *d_weights_bf16, int ldn, const float *d_bias,
-                              float alpha1, int *acc_out, int wide_rows = 0, int no_halo = 0) {
+                              float alpha1, int *acc_out, int wide_rows = 0, int no_halo = 0, int want_halo = 0) {
     TcPlan *plan = new TcPlan();
     memset(plan, 0, sizeof(*plan));
     TcParams &p = plan->p;
@@ -1586,8 +1646,9 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
         p.halo = halo ? 1 : 0;
         if (halo) { p.TW = 8; p.TH = 16; } else { p.TW = bestTW; p.TH = 128 / bestTW; }
         p.TWlog2 = 0; while ((1 << p.TWlog2) < p.TW) ++p.TWlog2;
+        p.jshift = halo ? 1 : 0;     // halo tiles start one merged row down: row 0 is a border row, and 2x2 windows then never straddle tiles
         p.xt = (p.OW + p.TW - 1) / p.TW;
-        p.jt = (int)((rows + p.TH - 1) / p.TH);
+        p.jt = (int)((rows - p.jshift + p.TH - 1) / p.TH);
         p.num_tiles = p.xt * p.jt * p.nt;
         // CTA pairs (cta_group::2) for the wide tiles: halves the B bytes each SM has to pull through its TMA unit
         p.cg = ((kind == 0 || ((kind == 1 || kind == 2) && !getenv("YB_TC_I8_CG1"))) && BN == 256 && p.xt * p.jt >= 2 &&
@@ -1627,7 +1688,7 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
     bool use_halo = false;
     if (l.size == 3 && l.stride == 1 && l.pad == 1 && !no_halo && !getenv("YB_TC_NO_HALO") && (kind == 0 || ((kind == 1 || kind == 2) && !getenv("YB_TC_I8_NO_HALO")))) {
         const double t_halo = layout(true), t_tap = layout(false);
-        use_halo = t_halo < 0.97 * t_tap || getenv("YB_TC_HALO") != nullptr;
+        use_halo = t_halo < 0.97 * t_tap || want_halo || getenv("YB_TC_HALO") != nullptr;   // want_halo: a fused max-pool needs the 8 x 16 tiles
     }
     layout(use_halo);
     // several K-blocks per stage when they are small: the single MMA-issuing thread pays a fixed barrier round
@@ -1811,18 +1872,31 @@ void tc_plan_fuse_yolo(void *vp, float *d_yolo_nchw, int classes) {
     plan->p.yolo_per = 4 + classes + 1;
 }
 
+// Fuse the following 2x2 / stride-2 max-pool and the next integer layer's input conversion into an integer-kind halo plan:
+// mode 1 = s8 quantised with `mult` (INT8 layer next), 2 = +-1 bytes (XNOR layer on the tensor cores next).  `qnext` is that layer's
+// s8 input (padded NHWC).  Returns 0 (and changes nothing) when the plan's tiling cannot do it.
+int tc_plan_fuse_pool(void *vp, int mode, float mult, const TV &qnext) {
+    TcPlan *plan = reinterpret_cast<TcPlan *>(vp);
+    TcParams &p = plan->p;
+    if (!(p.kind == 1 || p.kind == 2) || !p.halo || p.TW != 8 || p.jshift != 1 || (p.PR & 1) || (p.OW & 1) || (p.OH & 1) || p.acc_out) return 0;
+    if (qnext.H != p.OH / 2 || qnext.W != p.OW / 2 || qnext.ldc % 16 != 0 || (reinterpret_cast<uintptr_t>(qnext.base) & 15) || p.n % 32 != 0) return 0;
+    p.pool_mode = mode; p.pool_mult = mult;
+    p.pool_out = reinterpret_cast<signed char *>(qnext.base); p.pool_ldc = qnext.ldc; p.pool_Hp = qnext.Hp; p.pool_Wp = qnext.Wp;
+    return 1;
+}
+
 void *tc_make_plan_i8(const Layer &l, const TV &q, const TV &out, const void *d_weights_s8, int ldn, const float *d_bias,
-                      float alpha1, int *acc_out) {
+                      float alpha1, int *acc_out, int want_halo) {
     TV none{};
-    return make_plan_common(1, l, q, out, false, none, false, ACT_LINEAR, d_weights_s8, ldn, d_bias, alpha1, acc_out);
+    return make_plan_common(1, l, q, out, false, none, false, ACT_LINEAR, d_weights_s8, ldn, d_bias, alpha1, acc_out, 0, 0, want_halo);
 }
 
 // XNOR layer mapped onto kind::i8: activations and weights as +-1 bytes, so the s32 accumulator is 2*count - K.
 void *tc_make_plan_xnor(const Layer &l, const TV &q, const TV &out, const void *d_weights_pm1, int ldn, const float *d_bias,
-                        const float *d_mean, int *counts_out) {
+                        const float *d_mean, int *counts_out, int want_halo) {
     TV none{};
     TcPlan *plan = reinterpret_cast<TcPlan *>(
-        make_plan_common(2, l, q, out, false, none, false, ACT_LINEAR, d_weights_pm1, ldn, d_bias, 0.f, counts_out));
+        make_plan_common(2, l, q, out, false, none, false, ACT_LINEAR, d_weights_pm1, ldn, d_bias, 0.f, counts_out, 0, 0, want_halo));
     plan->p.mean = d_mean;
     plan->p.xK = l.size * l.size * l.c;
     return plan;

@@ -22,10 +22,12 @@ void *tc_make_plan_tf32(const Layer &l, const TV &in, const TV &out, const void 
 // INT8 (kind::i8) variant
 int tc_i8_supported(const Layer &l, const TV &q, const TV &out);
 void *tc_make_plan_i8(const Layer &l, const TV &q, const TV &out, const void *d_weights_s8, int ldn, const float *d_bias,
-                      float alpha1, int *acc_out);
+                      float alpha1, int *acc_out, int want_halo = 0);
 // XNOR layer as +-1 s8 on kind::i8 (q: s8 activation with -1 borders)
 void *tc_make_plan_xnor(const Layer &l, const TV &q, const TV &out, const void *d_weights_pm1, int ldn, const float *d_bias,
-                        const float *d_mean, int *counts_out);
+                        const float *d_mean, int *counts_out, int want_halo = 0);
+// fuse the following 2x2/2 max-pool + the next integer layer's input conversion (1: s8 quantised, 2: +-1 bytes) into an integer plan
+int tc_plan_fuse_pool(void *plan, int mode, float mult, const TV &qnext);
 // fuse the following [yolo] layer into the (f32-output) plan: logistic + NCHW store in the epilogue
 void tc_plan_fuse_yolo(void *plan, float *d_yolo_nchw, int classes);
 // K-split of the tail wave of a bf16 plan (wave quantisation): `ws` (tc_ksplit_ws_bytes) and `flags`

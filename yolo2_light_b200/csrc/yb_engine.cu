@@ -244,6 +244,20 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
     // not -1.  Same here: k_binarize_pm1 + the exact-order float convolution.
     auto xnor_fallback = [&](const Layer &l) { return l.xnor && !(l.stride == 1 && l.pad == 1); };
 
+    // integer conv i -> 2x2/2 max-pool i+1 -> integer conv i+2, nothing else reading i or i+1: the pool and the next layer's input
+    // conversion can run in conv i's epilogue (tc_plan_fuse_pool).  Returns the mode (1 s8 quantised, 2 +-1 bytes) or 0.
+    auto conv_pool_mode = [&](int i) -> int {
+        if (!opt.fuse || opt.keep_counts || getenv("YB_NO_CONV_POOL_FUSE") || i + 2 >= nl) return 0;
+        const Layer &mp = net->layers[i + 1], &c2 = net->layers[i + 2];
+        if (mp.type != YB_MAXPOOL || mp.size != 2 || mp.stride != 2 || mp.pad != 1 || c2.type != YB_CONVOLUTIONAL) return 0;
+        if (cons[i].size() != 1 || cons[i][0] != i + 1 || cons[i + 1].size() != 1 || cons[i + 1][0] != i + 2) return 0;
+        const int v2 = conv_variant(i + 2);
+        if (v2 == 2) return 1;
+        if (v2 == 1 && xnor_on_tc(c2) && !xnor_fallback(c2)) return 2;
+        if (v2 == 1 && !xnor_fallback(c2)) return 3;     // next XNOR layer reads sign bits (popcount kernels)
+        return 0;
+    };
+
     // ---- fusion plan: conv i + same-shape shortcut i+1 whose only reader is that shortcut -------------
     std::vector<int> fused_into(nl, -1);   // conv i writes layer fused_into[i]'s output
     std::vector<char> is_fused_sc(nl, 0);
@@ -413,6 +427,7 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
     std::vector<int> use_tc(nl, 0);
     e->not_materialised.assign(nl, 0);
     std::vector<char> prefilled(nl, 0);   // the producing max-pool already wrote this conv's s8 / sign input (fused)
+    std::vector<char> pool_in_conv(nl, 0); // this max-pool runs inside the epilogue of the integer convolution in front of it
     for (int i = 0; i < nl; ++i) {
         const Layer &l = net->layers[i];
         if (l.type != YB_CONVOLUTIONAL) continue;
@@ -549,7 +564,8 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                              (e->out_dt[0] == DT_F32 || (e->out_tv[0].ldc % 8 == 0));
         // exact nets: stem + 2x2/2 max-pool + the integer layer's input conversion in one kernel (k_stem_pool): layers 0 and 1
         // are then never written to HBM
-        bool pool_ok = stem_ok && opt.fuse && e->out_dt[0] == DT_F32 && l0.n == 16 && nl > 2 && !getenv("YB_NO_STEM_POOL_FUSE");
+        bool pool_ok = stem_ok && opt.fuse && e->out_dt[0] == DT_F32 && l0.n == 16 && nl > 2 && !getenv("YB_NO_STEM_POOL_FUSE") &&
+                       (l0.activation == YB_LEAKY || l0.activation == YB_LINEAR);
         if (pool_ok) {
             const Layer &mp = net->layers[1], &c2 = net->layers[2];
             pool_ok = mp.type == YB_MAXPOOL && mp.size == 2 && mp.stride == 2 && mp.pad == 1 && cons[0].size() == 1 && cons[0][0] == 1 &&
@@ -576,8 +592,11 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
             e->not_materialised[0] = e->not_materialised[1] = 1;
             e->first_kind = OP_CONV_SIMT; e->first_layer = 0;
             e->first_op = [=](const float *din, cudaStream_t s) {
-                if (v2 == 2) k_stem_pool<0><<<grid, 128, 0, s>>>(din, q, w16, act, H, W, mult, 0x8000000080000000ull);
-                else k_stem_pool<2><<<grid, 128, 0, s>>>(din, q, w16, act, H, W, mult, 0x8000000080000000ull);
+                const unsigned long long nz = 0x8000000080000000ull;
+                if (v2 == 2 && act == ACT_LEAKY) k_stem_pool<0, ACT_LEAKY><<<grid, 128, 0, s>>>(din, q, w16, act, H, W, mult, nz);
+                else if (v2 == 2) k_stem_pool<0, ACT_LINEAR><<<grid, 128, 0, s>>>(din, q, w16, act, H, W, mult, nz);
+                else if (act == ACT_LEAKY) k_stem_pool<2, ACT_LEAKY><<<grid, 128, 0, s>>>(din, q, w16, act, H, W, mult, nz);
+                else k_stem_pool<2, ACT_LINEAR><<<grid, 128, 0, s>>>(din, q, w16, act, H, W, mult, nz);
             };
         } else if (stem_ok && stem_w_off != (size_t)-1 && e->out_dt[0] == DT_BF16 && tc_stem_supported(l0, e->out_tv[0]) &&
             !getenv("YB_NO_STEM_TC")) {
@@ -743,8 +762,17 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                             e->ops.push_back(Op{OP_BINARIZE, i, [tin, q, g](cudaStream_t s) { k_binarize_s8<<<g, 256, 0, s>>>(tin, q); }});
                         void *plan = tc_make_plan_xnor(l, q, tout, e->w_arena + cw[i].w_s8, cw[i].ldn,
                                                        reinterpret_cast<const float *>(e->w_arena + cw[i].bias),
-                                                       reinterpret_cast<const float *>(e->w_arena + cw[i].mean), cnt_dbg);
+                                                       reinterpret_cast<const float *>(e->w_arena + cw[i].mean), cnt_dbg,
+                                                       conv_pool_mode(i) != 0);
                         e->tc_plans.push_back(plan);
+                        if (const int pm = conv_pool_mode(i)) {
+                            const Layer &c2 = net->layers[i + 2];
+                            TV qn = make_tv(e->act_arena + side_off[i + 2], B, c2.h, c2.w, c2.c, side_ld[i + 2], P, DT_S8, 0);
+                            if (tc_plan_fuse_pool(plan, pm, pm == 1 ? c2.input_quant_multipler : 0.f, qn)) {
+                                prefilled[i + 2] = 1; pool_in_conv[i + 1] = 1;
+                                e->not_materialised[i] = e->not_materialised[i + 1] = 1;
+                            }
+                        }
                         e->ops.push_back(Op{OP_CONV_TC_I8, i, [plan](cudaStream_t s) { tc_launch(plan, s); }});
                         break;
                     }
@@ -777,6 +805,23 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                     const unsigned gsm = (unsigned)((M + 127) / 128);
                     const size_t smem = (size_t)l.n * 9 * CW * 4;
                     const int cw1 = CW;
+                    const int pm = (cnt_dbg == nullptr) ? conv_pool_mode(i) : 0;
+                    if (pm == 2 || pm == 3) {
+                        // the 2x2 max-pool behind this layer and the next XNOR layer's sign extraction run in this kernel
+                        const Layer &c2 = net->layers[i + 2];
+                        const TV qn = (pm == 2) ? make_tv(e->act_arena + side_off[i + 2], B, c2.h, c2.w, c2.c, side_ld[i + 2], P, DT_S8, 0)
+                                                : make_tv(e->act_arena + side_off[i + 2], B, c2.h, c2.w, side_ld[i + 2], side_ld[i + 2], P, DT_BITS, 0);
+                        const unsigned gp = (unsigned)(((long)B * c2.h * c2.w + 127) / 128);
+                        prefilled[i + 2] = 1; pool_in_conv[i + 1] = 1;
+                        e->not_materialised[i] = e->not_materialised[i + 1] = 1;
+                        e->ops.push_back(Op{OP_CONV_XNOR, i, [p, qn, gp, smem, cw1, pm](cudaStream_t s) {
+                            if (cw1 == 1 && pm == 2) k_conv_xnor_smallk_pool<1, 2><<<gp, 128, smem, s>>>(p, qn);
+                            else if (cw1 == 1) k_conv_xnor_smallk_pool<1, 3><<<gp, 128, smem, s>>>(p, qn);
+                            else if (pm == 2) k_conv_xnor_smallk_pool<2, 2><<<gp, 128, smem, s>>>(p, qn);
+                            else k_conv_xnor_smallk_pool<2, 3><<<gp, 128, smem, s>>>(p, qn);
+                        }});
+                        break;
+                    }
                     e->ops.push_back(Op{OP_CONV_XNOR, i, [p, gsm, smem, cw1](cudaStream_t s) {
                         if (cw1 == 1) k_conv_xnor_smallk<1><<<gsm, 128, smem, s>>>(p);
                         else k_conv_xnor_smallk<2><<<gsm, 128, smem, s>>>(p);
@@ -806,8 +851,17 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                 if (!getenv("YB_NO_TC") && tc_i8_supported(l, q, tout)) {
                     // s8 x s8 -> s32 on tcgen05 (kind::i8); weights [ldn][taps][cpad] are already K-major
                     void *plan = tc_make_plan_i8(l, q, tout, e->w_arena + cw[i].w_s8, cw[i].ldn,
-                                                 reinterpret_cast<const float *>(e->w_arena + cw[i].bias), alpha1, acc_dbg);
+                                                 reinterpret_cast<const float *>(e->w_arena + cw[i].bias), alpha1, acc_dbg,
+                                                 conv_pool_mode(i) != 0);
                     e->tc_plans.push_back(plan);
+                    if (const int pm = conv_pool_mode(i)) {
+                        const Layer &c2 = net->layers[i + 2];
+                        TV qn = make_tv(e->act_arena + side_off[i + 2], B, c2.h, c2.w, c2.c, side_ld[i + 2], P, DT_S8, 0);
+                        if (tc_plan_fuse_pool(plan, pm, pm == 1 ? c2.input_quant_multipler : 0.f, qn)) {
+                            prefilled[i + 2] = 1; pool_in_conv[i + 1] = 1;
+                            e->not_materialised[i] = e->not_materialised[i + 1] = 1;
+                        }
+                    }
                     e->ops.push_back(Op{OP_CONV_TC_I8, i, [plan](cudaStream_t s) { tc_launch(plan, s); }});
                     break;
                 }
@@ -824,6 +878,7 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
             break;
         }
         case YB_MAXPOOL: {
+            if (pool_in_conv[i]) break;    // done in the epilogue of the integer convolution in front of it
             need_prev();
             const TV tout = e->out_tv[i];
             const int size = l.size, stride = l.stride, pad = l.pad;

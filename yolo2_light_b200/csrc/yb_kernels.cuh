@@ -374,6 +374,58 @@ struct XnorP {
     int32_t *counts;          // optional raw popcounts, NCHW (tests)
 };
 
+// The same convolution with the following 2x2 / stride-2 max-pool and the next XNOR layer's input conversion fused in: one thread
+// per POOLED pixel computes the four popcount outputs of its window for every filter, takes the reference's max (max-pool
+// semantics: elements outside the image are skipped) and writes only the SIGN the next layer would have extracted -- MODE 2: +-1
+// bytes (next layer runs as +-1 on kind::i8), MODE 3: sign bits (next layer on the popcount kernels).  The f32 activation and the
+// pooled f32 tensor are never written.  Bit-identical to conv -> max-pool -> binarise.
+template <int CW, int MODE>
+__global__ void __launch_bounds__(128) k_conv_xnor_smallk_pool(XnorP p, TV q /* next layer's input: s8 (MODE 2) or bit words (MODE 3) */) {
+    extern __shared__ uint32_t wsm[];            // [n][9*CW]
+    constexpr int KW = 9 * CW;
+    for (int i = threadIdx.x; i < p.n * KW; i += blockDim.x) wsm[i] = p.w[i];
+    __syncthreads();
+    const int H = p.out.H, W = p.out.W, PH = q.H, PW = q.W;
+    const long m = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (m >= (long)q.N * PH * PW) return;
+    const int px = (int)(m % PW), py = (int)((m / PW) % PH), n = (int)(m / ((long)PW * PH));
+    uint32_t a[16 * CW];                          // 4x4 window of input words around the 2x2 outputs
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const int iy = 2 * py + t / 4 - 1, ix = 2 * px + t % 4 - 1;
+        const bool in = iy >= -1 && iy <= H && ix >= -1 && ix <= W;      // the 1-pixel border exists in memory (words 0 == -1)
+        const uint32_t *src = tv_px<uint32_t>(p.bits, n, in ? iy : -1, in ? ix : -1);
+#pragma unroll
+        for (int c = 0; c < CW; ++c) a[t * CW + c] = in ? src[c] : 0u;
+    }
+    uint32_t word = 0;
+    for (int f = 0; f < p.n; ++f) {
+        const uint32_t *wf = wsm + f * KW;
+        float mx = -3.402823466e+38f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {             // window order of the reference: rows, then columns
+            const int dy = k >> 1, dx = k & 1;
+            if (2 * py + dy >= H || 2 * px + dx >= W) continue;
+            int cnt = 0;
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+#pragma unroll
+                for (int c = 0; c < CW; ++c) cnt += __popc(~(a[((t / 3 + dy) * 4 + t % 3 + dx) * CW + c] ^ wf[t * CW + c]));
+            const int count = cnt - p.padbits;
+            float v = __fadd_rn(__fmul_rn((float)(2 * count - p.K), p.mean[f]), p.bias[f]);
+            v = act_exact(v, p.act);
+            mx = v > mx ? v : mx;
+        }
+        if (MODE == 2) {     // four +-1 bytes per store (the filter count of an XNOR layer feeding the tensor-core path is a multiple of 32)
+            word |= (mx > 0.f ? 0x01u : 0xFFu) << (8 * (f & 3));
+            if ((f & 3) == 3) { reinterpret_cast<uint32_t *>(tv_px<int8_t>(q, n, py, px))[f >> 2] = word; word = 0; }
+        } else {
+            if (mx > 0.f) word |= 1u << (f & 31);
+            if ((f & 31) == 31 || f + 1 == p.n) { tv_px<uint32_t>(q, n, py, px)[f >> 5] = word; word = 0; }
+        }
+    }
+}
+
 // thread-per-(pixel, word) variant: each thread reads its 32 (or fewer) channels with 16-byte loads -- far fewer,
 // fatter threads than the ballot version; used whenever the channel vector is 16-byte aligned.
 template <typename TIn>
@@ -865,8 +917,10 @@ __device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsig
 // k_maxpool_fused.  Bit-identical to the three separate kernels.
 // MODE 0: s8 quantised (q.ldc bytes per pixel, channels >= 16 stay zero); 2: sign bits (one word per pixel).
 // ------------------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(128) k_stem_pool(const float *__restrict__ in, TV q, const __grid_constant__ StemW<16> sw, int act,
+// ACT is a template parameter: act_exact() with a run-time activation drags the double-precision logistic (exp) into each of the 64
+// call sites -- 19 k SASS instructions, 300 KB of code that no instruction cache holds.
+template <int MODE, int ACT>
+__global__ void __launch_bounds__(128) k_stem_pool(const float *__restrict__ in, TV q, const __grid_constant__ StemW<16> sw, int /*act*/,
                                                    int H, int W, float mult, unsigned long long negzero2 /* 0x8000000080000000 */) {
     constexpr int NF = 16;
     const int OH = q.H, OW = q.W;
@@ -917,7 +971,8 @@ __global__ void __launch_bounds__(128) k_stem_pool(const float *__restrict__ in,
 #pragma unroll
         for (int k = 0; k < 4; ++k) {                       // window order of the reference: rows, then columns
             const bool inside = (2 * py + (k >> 1)) < H && (2 * px + (k & 1)) < W;
-            const float v = act_exact(__fadd_rn(acc[k][f], sw.b[f]), act);
+            float v = __fadd_rn(acc[k][f], sw.b[f]);
+            if (ACT == ACT_LEAKY) v = (v > 0.f) ? v : (float)(0.1 * (double)v);     // activate(), additionally.h:91 (scalar build)
             if (inside) mx = v > mx ? v : mx;
         }
         m[f] = mx;
