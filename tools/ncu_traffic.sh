@@ -1,5 +1,5 @@
 #!/bin/bash
-# DRAM traffic of every k_conv_tc launch of one eager forward (yolov3 608 b16) -> profiles/r01_traffic.json
+# DRAM traffic of every k_conv_tc launch of one eager forward (yolov3 608 b16) -> profiles/r02_traffic.json
 set -e
 cd "$(dirname "$0")/.."
 export YB_NO_GRAPH=1
@@ -20,6 +20,6 @@ for r in rows[hi + 1:]:
     tot += float(r[mv].replace(",", "")) * scale.get(r[mu], 1); ids.add(r[idc])
 out = {"yolov3-608-fp32-b16": {"dram_bytes_per_launch": tot / max(len(ids), 1), "launches": len(ids), "total_bytes": tot,
                                "how": "ncu dram__bytes_read.sum + dram__bytes_write.sum over every k_conv_tc<2> launch (the dominant kernel) of one eager forward"}}
-json.dump(out, open("profiles/r01_traffic.json", "w"), indent=1); json.dump(out, open("gpurun_out/r01_traffic.json", "w"), indent=1)
+json.dump(out, open("profiles/r02_traffic.json", "w"), indent=1); json.dump(out, open("gpurun_out/r02_traffic.json", "w"), indent=1)
 print(out)
 PY

@@ -235,7 +235,11 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
     auto xnor_on_tc = [&](const Layer &l) {
         const char *ev = getenv("YB_XNOR_TC");
         if (ev && ev[0] == '0') return false;
-        return l.xnor && l.c % 32 == 0 && l.c >= 64 && l.size == 3 && l.stride == 1 && l.pad == 1 && l.n >= 8;
+        // channels are padded to a multiple of 32 with zero WEIGHT bytes (whatever the activation pad bytes hold contributes 0), so
+        // even the 16- and 32-channel layers run here: the popcount kernels are bound by the 16 POPC/clk/SM of the integer pipe
+        // (round 1: 79-85 % of that rate), the same layers as +-1 on kind::i8 take 0.55-0.75 of the time (profiles/r02_notes.md)
+        const int minc = getenv("YB_XNOR_TC_MINC") ? atoi(getenv("YB_XNOR_TC_MINC")) : 16;
+        return l.xnor && l.c % 16 == 0 && l.c >= minc && l.size == 3 && l.stride == 1 && l.pad == 1 && l.n >= 8;
     };
 
     // XNOR layers with stride != 1 or pad != 1 never reach the bit GEMM in the reference: forward_convolutional_layer_cpu
@@ -344,7 +348,7 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
             side_off[i] = act_total;
             act_total += align_up(tv_bytes(B, l.h, l.w, side_ld[i], P, DT_F32), 1024);
         } else if (v == 1 && xnor_on_tc(l)) {
-            side_ld[i] = l.c;   // +-1 bytes
+            side_ld[i] = (int)align_up(l.c, 32);   // +-1 bytes; pad channels meet zero weights
             side_off[i] = act_total;
             act_total += align_up(tv_bytes(B, l.h, l.w, side_ld[i], P, DT_S8), 1024);
         } else if (v == 1) {
@@ -492,15 +496,15 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                     for (int t = 0; t < taps; ++t)
                         dst[((size_t)c * taps + t) * w.ldw + f] = l.weights[((size_t)f * l.c + c) * taps + t] > 0 ? l.mean_arr[f] : -l.mean_arr[f];
         } else if (v == 1 && xnor_on_tc(l)) {
-            // +-1 bytes [ldn][taps][C]: +1 where w > 0, -1 otherwise; padded filter rows stay 0
-            w.cpad = l.c;
+            // +-1 bytes [ldn][taps][cpad]: +1 where w > 0, -1 otherwise; padded filter rows and padded channels stay 0
+            w.cpad = side_ld[i];
             w.ldn = (int)align_up(l.n, 64);
-            w.w_s8 = reserve((size_t)w.ldn * taps * l.c);
+            w.w_s8 = reserve((size_t)w.ldn * taps * w.cpad);
             int8_t *dst = reinterpret_cast<int8_t *>(&hostw[w.w_s8]);
             for (int f = 0; f < l.n; ++f)
                 for (int c = 0; c < l.c; ++c)
                     for (int t = 0; t < taps; ++t)
-                        dst[((size_t)f * taps + t) * l.c + c] = l.weights[((size_t)f * l.c + c) * taps + t] > 0 ? 1 : -1;
+                        dst[((size_t)f * taps + t) * w.cpad + c] = l.weights[((size_t)f * l.c + c) * taps + t] > 0 ? 1 : -1;
             w.mean = reserve(sizeof(float) * align_up(l.n, 64));
             memcpy(&hostw[w.mean], l.mean_arr.data(), sizeof(float) * l.n);
         } else if (v == 1) {
@@ -570,15 +574,15 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
             const Layer &mp = net->layers[1], &c2 = net->layers[2];
             pool_ok = mp.type == YB_MAXPOOL && mp.size == 2 && mp.stride == 2 && mp.pad == 1 && cons[0].size() == 1 && cons[0][0] == 1 &&
                       cons[1].size() == 1 && cons[1][0] == 2 && c2.type == YB_CONVOLUTIONAL && conv_variant(2) != 0 &&
-                      side_off[2] != (size_t)-1 && !xnor_fallback(c2) && !(conv_variant(2) == 1 && xnor_on_tc(c2)) &&
-                      (conv_variant(2) == 1 || side_ld[2] % 16 == 0);
+                      side_off[2] != (size_t)-1 && !xnor_fallback(c2) && (conv_variant(2) == 1 && !xnor_on_tc(c2) ? true : side_ld[2] % 16 == 0);
         }
         if (pool_ok) {
             stem_fused = true; stem_pool_fused = true;
             const Layer &c2 = net->layers[2];
             const int v2 = conv_variant(2);
-            const TV q = (v2 == 2) ? make_tv(e->act_arena + side_off[2], B, c2.h, c2.w, c2.c, side_ld[2], P, DT_S8, 0)
-                                   : make_tv(e->act_arena + side_off[2], B, c2.h, c2.w, side_ld[2], side_ld[2], P, DT_BITS, 0);
+            const bool pm1 = v2 == 1 && xnor_on_tc(c2);      // next layer reads +-1 bytes
+            const TV q = (v2 == 2 || pm1) ? make_tv(e->act_arena + side_off[2], B, c2.h, c2.w, c2.c, side_ld[2], P, DT_S8, 0)
+                                          : make_tv(e->act_arena + side_off[2], B, c2.h, c2.w, side_ld[2], side_ld[2], P, DT_BITS, 0);
             StemW<16> w16{};
             for (int f = 0; f < 16; ++f) {
                 for (int c = 0; c < 3; ++c)
@@ -595,6 +599,8 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                 const unsigned long long nz = 0x8000000080000000ull;
                 if (v2 == 2 && act == ACT_LEAKY) k_stem_pool<0, ACT_LEAKY><<<grid, 128, 0, s>>>(din, q, w16, act, H, W, mult, nz);
                 else if (v2 == 2) k_stem_pool<0, ACT_LINEAR><<<grid, 128, 0, s>>>(din, q, w16, act, H, W, mult, nz);
+                else if (pm1 && act == ACT_LEAKY) k_stem_pool<1, ACT_LEAKY><<<grid, 128, 0, s>>>(din, q, w16, act, H, W, mult, nz);
+                else if (pm1) k_stem_pool<1, ACT_LINEAR><<<grid, 128, 0, s>>>(din, q, w16, act, H, W, mult, nz);
                 else if (act == ACT_LEAKY) k_stem_pool<2, ACT_LEAKY><<<grid, 128, 0, s>>>(din, q, w16, act, H, W, mult, nz);
                 else k_stem_pool<2, ACT_LINEAR><<<grid, 128, 0, s>>>(din, q, w16, act, H, W, mult, nz);
             };
@@ -755,7 +761,7 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                 }
                 const bool in_vec = (tin.ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(tin.base) & 15) == 0;
                 if (xnor_on_tc(l) && in_vec) {
-                    TV q = make_tv(e->act_arena + side_off[i], B, l.h, l.w, l.c, l.c, P, DT_S8, 0);
+                    TV q = make_tv(e->act_arena + side_off[i], B, l.h, l.w, l.c, side_ld[i], P, DT_S8, 0);
                     if (tc_i8_supported(l, q, tout)) {
                         const int g = grid_for((long)B * l.h * l.w * (l.c / 16));
                         if (!prefilled[i])
@@ -896,8 +902,8 @@ std::shared_ptr<Engine> build_engine(Network *net, const EngineOptions &opt) {
                     e->ops.push_back(Op{OP_MAXPOOL, i, [tin, q, size, stride, pad, mult, g](cudaStream_t s) {
                         k_maxpool_fused<0><<<g, 256, 0, s>>>(tin, q, size, stride, pad, mult); }});
                 } else if (xnor_on_tc(c)) {
-                    TV q = make_tv(e->act_arena + side_off[i + 1], B, c.h, c.w, c.c, c.c, P, DT_S8, 0);
-                    const int g = grid_for((long)B * c.h * c.w * (c.c / 4));
+                    TV q = make_tv(e->act_arena + side_off[i + 1], B, c.h, c.w, c.c, side_ld[i + 1], P, DT_S8, 0);
+                    const int g = grid_for((long)B * c.h * c.w * (q.ldc / 4));
                     e->ops.push_back(Op{OP_MAXPOOL, i, [tin, q, size, stride, pad, g](cudaStream_t s) {
                         k_maxpool_fused<1><<<g, 256, 0, s>>>(tin, q, size, stride, pad, 0.f); }});
                 } else {

@@ -915,7 +915,7 @@ __device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsig
 // reference's exact order (c, ky, kx; separately rounded products and sums: k_conv_stem<EXACT>), bias + activation, the
 // reference's max (forward_maxpool_layer_avx scalar semantics: -FLT_MAX start, strict >), then quant_i8 / sign exactly as
 // k_maxpool_fused.  Bit-identical to the three separate kernels.
-// MODE 0: s8 quantised (q.ldc bytes per pixel, channels >= 16 stay zero); 2: sign bits (one word per pixel).
+// MODE 0: s8 quantised (q.ldc bytes per pixel, channels >= 16 stay zero); 1: +-1 bytes; 2: sign bits (one word per pixel).
 // ------------------------------------------------------------------------------------------------------
 // ACT is a template parameter: act_exact() with a run-time activation drags the double-precision logistic (exp) into each of the 64
 // call sites -- 19 k SASS instructions, 300 KB of code that no instruction cache holds.
@@ -984,6 +984,16 @@ __global__ void __launch_bounds__(128) k_stem_pool(const float *__restrict__ in,
             uint32_t word = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) word |= (uint32_t)(quant_i8(m[g * 4 + j], mult) & 0xff) << (8 * j);
+            wq[g] = word;
+        }
+        *reinterpret_cast<uint4 *>(tv_px<int8_t>(q, n, py, px)) = make_uint4(wq[0], wq[1], wq[2], wq[3]);
+    } else if (MODE == 1) {     // +-1 bytes: the next XNOR layer runs as +-1 on kind::i8
+        uint32_t wq[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            uint32_t word = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) word |= (m[g * 4 + j] > 0.f ? 0x01u : 0xFFu) << (8 * j);
             wq[g] = word;
         }
         *reinterpret_cast<uint4 *>(tv_px<int8_t>(q, n, py, px)) = make_uint4(wq[0], wq[1], wq[2], wq[3]);
