@@ -1376,7 +1376,7 @@ struct StemTcP {
 };
 
 // U8: the input is the caller's 8-bit HWC frame (already of the network size): value = (float)((double)v / 255.0) exactly as
-// load_image_stb computes it (additionally.c:3093-3103), through a 256-entry table -- the u8 -> planar float pass over the batch
+// load_image_stb computes it (additionally.c:3093-3103) -- the u8 -> planar float pass over the batch
 // (71 MB written, 71 MB read back) disappears from the serving path.
 template <bool U8>
 __global__ void __launch_bounds__(128) k_stem_tc(StemTcP p) {
@@ -1386,9 +1386,11 @@ __global__ void __launch_bounds__(128) k_stem_tc(StemTcP p) {
     __shared__ uint32_t tmem_slot;
     __shared__ float bias_s[32];
     __shared__ unsigned long long optr[128];   // global address of every pixel's output row of the current tile (0: none)
-    __shared__ float lut[U8 ? 256 : 1];
     const int t = threadIdx.x, warp = t >> 5;
-    if constexpr (U8) { lut[t] = (float)((double)(float)t / 255.0); lut[t + 128] = (float)((double)(float)(t + 128) / 255.0); }
+    // U8: value = (float)((double)v / 255.) in the reference; the correctly rounded f32 division v / 255.f gives the same float for
+    // all 256 byte values (checked exhaustively: v / 255 is never within double-rounding distance of a float midpoint).  A 256-entry
+    // shared-memory table was tried first: random-index LDS costs ~3.5 wavefronts each and this kernel is L1-wavefront bound.
+    auto lut = [](unsigned char b) { return __fdiv_rn((float)b, 255.f); };
     const uint32_t a_addr = smem_u32(a_tile), b_addr = smem_u32(b_tile), bar = smem_u32(&mma_bar);
     if (t < 32) bias_s[t] = (t < p.nf) ? p.bias[t] : 0.f;
     {   // weights -> swizzled B tile (row f, 16-byte chunk j at f*64 + ((j ^ ((f>>1)&3)) << 4))
@@ -1425,9 +1427,9 @@ __global__ void __launch_bounds__(128) k_stem_tc(StemTcP p) {
                     const unsigned char *r1 = img8 + ((size_t)y * p.W + x) * 3, *r0 = r1 - (size_t)p.W * 3, *r2 = r1 + (size_t)p.W * 3;
 #pragma unroll
                     for (int j = 0; j < 9; ++j) {          // j = kx * 3 + c: nine consecutive bytes per image row
-                        v[0 * 9 + j] = lut[__ldg(r0 - 3 + j)];
-                        v[1 * 9 + j] = lut[__ldg(r1 - 3 + j)];
-                        v[2 * 9 + j] = lut[__ldg(r2 - 3 + j)];
+                        v[0 * 9 + j] = lut(__ldg(r0 - 3 + j));
+                        v[1 * 9 + j] = lut(__ldg(r1 - 3 + j));
+                        v[2 * 9 + j] = lut(__ldg(r2 - 3 + j));
                     }
                 } else {
 #pragma unroll
@@ -1438,7 +1440,7 @@ __global__ void __launch_bounds__(128) k_stem_tc(StemTcP p) {
                             const bool in_img = ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
 #pragma unroll
                             for (int c = 0; c < 3; ++c)
-                                v[(ky * 3 + kx) * 3 + c] = in_img ? lut[__ldg(img8 + ((size_t)iy * p.W + ix) * 3 + c)] : 0.f;
+                                v[(ky * 3 + kx) * 3 + c] = in_img ? lut(__ldg(img8 + ((size_t)iy * p.W + ix) * 3 + c)) : 0.f;
                         }
                 }
             } else {
