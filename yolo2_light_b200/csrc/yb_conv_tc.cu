@@ -596,24 +596,20 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                                 issue_kb(d_tmem, lo(a_tile + (uint32_t)(t / 3) * pitch + (uint32_t)(t % 3) * rb), ahi,
                                          lo(b0 + (uint32_t)t * bstep), (uint32_t)(cb | t));
                         } else {
-                            for (int ky = 0; ky < 3; ++ky) {        // one filter row = three K-blocks per batch
-                                uint32_t blo[3], ebar[3];
+                            for (int ky = 0; ky < 3; ++ky) {        // one filter row = three K-blocks of straight-line code
+                                const uint32_t a_row = a_tile + (uint32_t)ky * pitch;
+                                // each stage is waited for right in front of its own MMAs and released right behind them (a commit
+                                // covers everything issued before it).  Waiting for all three stages first made a 5-stage ring stall
+                                // once per batch: only two of the next three stages can be in flight while a batch executes
+                                // (role counters: MMA thread 62 % in wait_full at 75 % tensor utilisation, profiles/r02_notes.md).
 #pragma unroll
                                 for (int kx = 0; kx < 3; ++kx) {
                                     wait_full(stage, phase);
-                                    blo[kx] = lo(smem0 + (uint32_t)stage * stage_bytes);
-                                    ebar[kx] = empty_bar(stage);
+                                    tc_fence_after();
+                                    issue_kb(d_tmem, lo(a_row + (uint32_t)kx * rb), ahi, lo(smem0 + (uint32_t)stage * stage_bytes),
+                                             (uint32_t)(cb | ky | kx));
+                                    release(empty_bar(stage));
                                     if (++stage == stages) { stage = 0; phase ^= 1u; }
-                                }
-                                tc_fence_after();
-                                const uint32_t a_row = a_tile + (uint32_t)ky * pitch;
-                                // each stage's commit right behind its own MMAs (a commit covers everything issued before it: issued at
-                                // the end of the batch, all three stages would come free together and a ring shallower than 2 batches
-                                // + 1 would stall once per batch -- measured: +40 % on the deep-K layers with 5 stages)
-#pragma unroll
-                                for (int kx = 0; kx < 3; ++kx) {
-                                    issue_kb(d_tmem, lo(a_row + (uint32_t)kx * rb), ahi, blo[kx], (uint32_t)(cb | ky | kx));
-                                    release(ebar[kx]);
                                 }
                             }
                         }
@@ -634,46 +630,20 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     int kb0 = kb_begin;
                     while (kb0 < kb_end) {
                         // one batch = the K-blocks of one stage (sps > 1) or of two consecutive stages (sps == 1): up to 4 entries
-                        uint32_t alo[4], blo[4], ebar[2];
-                        int ne = 0, nst = 1;
-                        {   // first (or only) stage of the batch: entries 0 .. nsub-1
-                            const int nsub = min(sps, kb_end - kb0);
-                            wait_full(stage, phase);
-                            const uint32_t a_base = smem0 + (uint32_t)stage * stage_bytes, b_base = a_base + b_off;
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                alo[j] = lo(a_base + (uint32_t)j * a_bytes);
-                                blo[j] = lo(bstat ? smemB + (uint32_t)(kb0 + j) * b_bytes : b_base + (uint32_t)j * b_bytes);
-                            }
-                            ne = nsub;
-                            ebar[0] = empty_bar(stage);
-                            kb0 += nsub;
-                            if (++stage == stages) { stage = 0; phase ^= 1u; }
-                        }
-                        if (sps == 1 && kb0 < kb_end) {   // one K-block per stage: take the next stage into the same batch (entry 1)
-                            wait_full(stage, phase);
-                            const uint32_t a_base = smem0 + (uint32_t)stage * stage_bytes;
-                            alo[1] = lo(a_base);
-                            blo[1] = lo(bstat ? smemB + (uint32_t)kb0 * b_bytes : a_base + b_off);
-                            ne = 2; nst = 2;
-                            ebar[1] = empty_bar(stage);
-                            kb0 += 1;
-                            if (++stage == stages) { stage = 0; phase ^= 1u; }
-                        } else ebar[1] = 0u;
+                        // one pipeline stage = up to 4 K-blocks (sps): wait, issue its MMAs in straight-line code, release it
+                        const int nsub = min(sps, kb_end - kb0);
+                        wait_full(stage, phase);
                         tc_fence_after();
-                        const uint32_t first = (uint32_t)(kb0 - kb_begin - ne);   // 0 on the first K-block of the segment: overwrite
-                        // frees the smem stages (in both CTAs) when their MMAs retire: each stage's commit right behind its own MMAs
-                        if (nst == 2) {
-                            issue_kb(d_tmem, alo[0], ahi, blo[0], first);
-                            release(ebar[0]);
-                            issue_kb(d_tmem, alo[1], ahi, blo[1], 1u);
-                            release(ebar[1]);
-                        } else {
+                        const uint32_t a_base = smem0 + (uint32_t)stage * stage_bytes, b_base = a_base + b_off;
+                        const uint32_t first = (uint32_t)(kb0 - kb_begin);   // 0 on the first K-block of the segment: overwrite
 #pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if (e < ne) issue_kb(d_tmem, alo[e], ahi, blo[e], first | (uint32_t)e);
-                            release(ebar[0]);
-                        }
+                        for (int j = 0; j < 4; ++j)
+                            if (j < nsub)
+                                issue_kb(d_tmem, lo(a_base + (uint32_t)j * a_bytes), ahi,
+                                         lo(bstat ? smemB + (uint32_t)(kb0 + j) * b_bytes : b_base + (uint32_t)j * b_bytes), first | (uint32_t)j);
+                        release(empty_bar(stage));     // frees the smem stage (in both CTAs) when these MMAs retire
+                        kb0 += nsub;
+                        if (++stage == stages) { stage = 0; phase ^= 1u; }
                     }
                     release(tfull_bar(acc));     // accumulator complete -> epilogue warps (of both CTAs)
                     if (++acc == TC_ACC) { acc = 0; acc_phase ^= 1u; }
@@ -1376,7 +1346,8 @@ struct StemTcP {
 };
 
 // U8: the input is the caller's 8-bit HWC frame (already of the network size): value = (float)((double)v / 255.0) exactly as
-// load_image_stb computes it (additionally.c:3093-3103) -- the u8 -> planar float pass over the batch
+// load_image_stb computes it (additionally.c:3093-3103), through a 256-entry table (the correctly rounded f32 division v / 255.f
+// gives the same 256 floats, but ~8 instructions per value made this issue-bound kernel 0.3 ms slower) -- the u8 -> planar float pass over the batch
 // (71 MB written, 71 MB read back) disappears from the serving path.
 template <bool U8>
 __global__ void __launch_bounds__(128) k_stem_tc(StemTcP p) {
@@ -1386,11 +1357,9 @@ __global__ void __launch_bounds__(128) k_stem_tc(StemTcP p) {
     __shared__ uint32_t tmem_slot;
     __shared__ float bias_s[32];
     __shared__ unsigned long long optr[128];   // global address of every pixel's output row of the current tile (0: none)
+    __shared__ float lut[U8 ? 256 : 1];
     const int t = threadIdx.x, warp = t >> 5;
-    // U8: value = (float)((double)v / 255.) in the reference; the correctly rounded f32 division v / 255.f gives the same float for
-    // all 256 byte values (checked exhaustively: v / 255 is never within double-rounding distance of a float midpoint).  A 256-entry
-    // shared-memory table was tried first: random-index LDS costs ~3.5 wavefronts each and this kernel is L1-wavefront bound.
-    auto lut = [](unsigned char b) { return __fdiv_rn((float)b, 255.f); };
+    if constexpr (U8) { lut[t] = (float)((double)(float)t / 255.0); lut[t + 128] = (float)((double)(float)(t + 128) / 255.0); }
     const uint32_t a_addr = smem_u32(a_tile), b_addr = smem_u32(b_tile), bar = smem_u32(&mma_bar);
     if (t < 32) bias_s[t] = (t < p.nf) ? p.bias[t] : 0.f;
     {   // weights -> swizzled B tile (row f, 16-byte chunk j at f*64 + ((j ^ ((f>>1)&3)) << 4))
@@ -1427,9 +1396,9 @@ __global__ void __launch_bounds__(128) k_stem_tc(StemTcP p) {
                     const unsigned char *r1 = img8 + ((size_t)y * p.W + x) * 3, *r0 = r1 - (size_t)p.W * 3, *r2 = r1 + (size_t)p.W * 3;
 #pragma unroll
                     for (int j = 0; j < 9; ++j) {          // j = kx * 3 + c: nine consecutive bytes per image row
-                        v[0 * 9 + j] = lut(__ldg(r0 - 3 + j));
-                        v[1 * 9 + j] = lut(__ldg(r1 - 3 + j));
-                        v[2 * 9 + j] = lut(__ldg(r2 - 3 + j));
+                        v[0 * 9 + j] = lut[__ldg(r0 - 3 + j)];
+                        v[1 * 9 + j] = lut[__ldg(r1 - 3 + j)];
+                        v[2 * 9 + j] = lut[__ldg(r2 - 3 + j)];
                     }
                 } else {
 #pragma unroll
@@ -1440,7 +1409,7 @@ __global__ void __launch_bounds__(128) k_stem_tc(StemTcP p) {
                             const bool in_img = ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
 #pragma unroll
                             for (int c = 0; c < 3; ++c)
-                                v[(ky * 3 + kx) * 3 + c] = in_img ? lut(__ldg(img8 + ((size_t)iy * p.W + ix) * 3 + c)) : 0.f;
+                                v[(ky * 3 + kx) * 3 + c] = in_img ? lut[__ldg(img8 + ((size_t)iy * p.W + ix) * 3 + c)] : 0.f;
                         }
                 }
             } else {
