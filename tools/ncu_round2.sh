@@ -21,4 +21,7 @@ bash tools/ncu_traffic.sh
 for f in r02_yolov3_608_b16_all_convs r02_int8_tiny416_b64_convs r02_xnor_416_b64_convs r02_xnor_416_b64_popcount_only; do
   python tools/ncu_kernels.py gpurun_out/$f.ncu-rep > gpurun_out/${f}_summary.txt 2>&1
 done
-ls -la gpurun_out/r02_*.ncu-rep gpurun_out/r02_*summary.txt
+# gpurun merges at most 64 MiB back: keep the one report with source (the dominant kernel) and the text summaries of the rest
+rm -f gpurun_out/r02_yolov3_608_b16_all_convs.ncu-rep gpurun_out/r02_int8_tiny416_b64_convs.ncu-rep gpurun_out/r02_xnor_416_b64_convs.ncu-rep \
+      gpurun_out/r02_xnor_416_b64_popcount_only.ncu-rep
+ls -la gpurun_out/r02_*
