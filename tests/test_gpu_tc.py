@@ -96,6 +96,44 @@ def test_tc_every_layer_vs_oracle_on_bf16_inputs(size, batch, workdir):
     assert n_tc >= 14, n_tc
 
 
+def s2net():
+    """3x3 / stride-2 layers with 32 and 64 input channels: the parity-halo form of k_conv_tc (TcParams::halo == 2), with the
+    resident filter matrix (C = 32) and with streamed filter tiles over two channel blocks (C = 64), BN 64 / 128."""
+    c = cfgs._conv
+    return [cfgs._net(64, 64),
+            c(32, 3),                   # 0 stem
+            c(64, 3, 2),                # 1 C=32 s2, filters resident
+            c(64, 3, 2),                # 2 C=64 s2, BN 64
+            c(128, 3, 2),               # 3 C=64 s2, BN 128
+            c(255, 1, bn=False, act="linear"),
+            cfgs._yolo("0,1,2", cfgs.COCO_ANCHORS, 9)]
+
+
+@pytest.mark.parametrize("hw,batch,per_tap", [((64, 64), 2, 0), ((96, 160), 3, 0), ((80, 48), 5, 0), ((608, 32), 1, 0), ((96, 160), 3, 1)])
+def test_tc_stride2_parity_halo_vs_oracle(hw, batch, per_tap, workdir, monkeypatch):
+    import yolo2_light_b200 as yb
+    from oracle import port
+    h, w = hw
+    secs = s2net()
+    secs[0][1]["height"], secs[0][1]["width"] = str(h), str(w)
+    cfg, wts = _files(workdir, f"s2net{h}x{w}", secs, 31)
+    if per_tap:
+        monkeypatch.setenv("YB_TC_S2_HALO_MAXC", "0")   # the one-box-per-tap form of the same layers
+    net = yb.load_network(cfg, wts, batch=batch)
+    net.set_precision(yb.YB_PREC_BF16_TC)
+    net.set_option("fuse", 0)
+    x = cfgs.synthetic_images(batch, 3, h, w, seed=9)
+    net.predict(x)
+    layers = net.layers
+    got = [net.fetch_layer(i) for i in range(net.n)]
+    for i in (1, 2, 3):
+        l = layers[i]
+        exp = bf16_round(port.conv_fp32(got[i - 1], bf16_round(l["weights"]), l["biases"], l["n"], l["size"], l["stride"], l["pad"],
+                                        l["activation"]))
+        err = util.rel_l2(got[i], exp)
+        assert err <= 5e-4, (hw, i, err)
+
+
 def test_tc_fused_equals_unfused(workdir):
     import yolo2_light_b200 as yb
     cfg, wts = _files(workdir, "tcnet64f", tcnet(64), 22)

@@ -79,8 +79,12 @@ struct TcParams {
     // the 8-row groups (TW+2) lines apart (descriptor SBO).  tcgen05 applies the swizzle to absolute address bits, so any start
     // line and any SBO work (tools/probes/desc_probe.cu, profiles/r02_desc_probe.txt).  TMA bytes of A per K-block: 1/6.4 of
     // the one-box-per-tap scheme.  A ring: a_stages x a_stage_bytes; the B ring keeps `stages` x b_bytes.
+    // halo == 2 (3x3 / stride 2 / pad 1, C <= 64): the same idea on the four parity planes of the padded input -- output (ox, oy)
+    // reads padded pixel (2 ox + kx, 2 oy + ky), i.e. half-pixel (ox + (kx >> 1), oy + (ky >> 1)) of plane (ky & 1, kx & 1).  Four
+    // [TH+1][TW+1] x BK boxes per channel block (one per plane, a_stage_bytes / 4 apart) replace nine [TH][TW] boxes: 0.53 of
+    // the TMA bytes, which is what bound these layers (producer 47 % in TMA issue, MMA thread 34-50 % waiting for data).
     int halo, a_stages;
-    uint32_t a_stage_bytes, halo_bytes, halo_pitch;   // halo_pitch = (TW+2) * row bytes
+    uint32_t a_stage_bytes, halo_bytes, halo_pitch;   // halo_pitch = (TW+2) * row bytes (halo == 2: (TW+1) * row bytes)
     uint32_t desc_hi_a;                       // descriptor high word of the halo A operand (SBO = halo_pitch)
     // TMA epilogue (bf16 output, stride 1, BN >= 128): each group of four epilogue warps writes its 128 x 64-column slab as
     // bf16 into a 128B-swizzled shared-memory tile and one thread stores it with cp.async.bulk.tensor; the shortcut residual
@@ -90,6 +94,10 @@ struct TcParams {
     // BN columns) instead of half the columns of every tile -- two tiles are in the epilogue at once; the per-tile epilogue of the
     // small tiles is a latency chain (TMEM load -> math -> barrier -> store), not a throughput problem.
     int epi_alt;
+    // epi_bufs (TMA epilogue): OUT tiles per warp group.  With one tile a slab cannot be written before the bulk store of the previous
+    // slab has finished READING the tile, which put the store's issue-to-read latency on the critical path of every slab of the
+    // shallow-K layers; with two the group only waits for the store before the last one.
+    int epi_bufs;
     // Fused 2x2 / stride-2 max-pool + input conversion of the NEXT integer layer (integer kinds, halo tiles of 8 x 16 pixels):
     // the epilogue reduces every 2x2 window inside the warp (lane ^ 1 = x neighbour, lane ^ 8 = y neighbour), quantises (pool_mode
     // 1: quant_i8 with pool_mult) or takes the sign (pool_mode 2: +-1 bytes) and writes bytes straight into the next layer's s8
@@ -111,7 +119,7 @@ struct TcParams {
     const char *res; long res_ldc; int res_bf16;
     const float *bias; int act, act2;
     uint32_t tmem_cols;
-    unsigned long long *stats; // YB_TC_STATS=1: per-CTA cycle counters [grid][8] (diagnostic)
+    unsigned long long *stats; // YB_TC_STATS=1: per-CTA cycle counters [grid][16] (diagnostic)
     int no_coalesce;          // YB_TC_NO_COALESCE=1: per-thread row stores (the pre-staging epilogue), for A/B comparison
     int dbg;                  // YB_TC_DBG bit mask for bottleneck experiments: 1 no TMA, 2 no MMA, 4 no epilogue memory ops
 };
@@ -178,6 +186,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap *tm, uint32_t src
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -450,7 +459,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     const uint32_t fb = fullA_bar(sa);
                     if (leader) mbar_arrive_expect_tx(fb, (uint32_t)CG * halo_bytes);
                     const uint32_t ad = smemA + (uint32_t)sa * a_stage_bytes;
-                    if constexpr (CG == 2) tma2_load_3d(ad, &tmA, fb, cbA * BK, x0, J0 - 1);
+                    if (p.halo == 2) {
+                        const uint32_t plane = a_stage_bytes >> 2;
+#pragma unroll
+                        for (int pl = 0; pl < 4; ++pl) {
+                            if constexpr (CG == 2) tma2_load_5d(ad + (uint32_t)pl * plane, &tmA, fb, cbA * BK, pl & 1, x0, pl >> 1, J0);
+                            else tma_load_5d(ad + (uint32_t)pl * plane, &tmA, fb, cbA * BK, pl & 1, x0, pl >> 1, J0);
+                        }
+                    } else if constexpr (CG == 2) tma2_load_3d(ad, &tmA, fb, cbA * BK, x0, J0 - 1);
                     else tma_load_3d(ad, &tmA, fb, cbA * BK, x0, J0 - 1);
                     ++cbA;
                     if (++sa == SA) { sa = 0; pha ^= 1u; }
@@ -524,7 +540,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 }
             }
             }
-            if (ST && p.stats) { p.stats[blockIdx.x * 8 + 0] = (unsigned long long)w_empty; p.stats[blockIdx.x * 8 + 1] = (unsigned long long)(clock64() - t_begin); p.stats[blockIdx.x * 8 + 7] = (unsigned long long)w_tma; }
+            if (ST && p.stats) { p.stats[blockIdx.x * 16 + 0] = (unsigned long long)w_empty; p.stats[blockIdx.x * 16 + 1] = (unsigned long long)(clock64() - t_begin); p.stats[blockIdx.x * 16 + 7] = (unsigned long long)w_tma; }
         }
     } else if (warp == 1) {
         // ======================= MMA issuer (CG=2: the leader CTA only, for both CTAs) =======================
@@ -575,8 +591,20 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 // ---- halo mode: per channel block one activation tile (with halo) and nine filter tiles; tap (ky, kx) reads the
                 // activation tile from line ky*(TW+2) + kx on
                 const int SA = p.a_stages, cblocks = p.cblocks;
-                const uint32_t a_stage_bytes = p.a_stage_bytes, pitch = p.halo_pitch, rb = pitch / (uint32_t)(p.TW + 2);
+                const uint32_t a_stage_bytes = p.a_stage_bytes, pitch = p.halo_pitch, rb = pitch / (uint32_t)(p.TW + (p.halo == 2 ? 1 : 2));
                 const uint32_t ahi = p.desc_hi_a;
+                // byte offset of tap (ky, kx) inside the activation tile: line ky*(TW+2) + kx, or (stride 2) plane (ky&1, kx&1),
+                // line (ky>>1)*(TW+1) + (kx>>1)
+                uint32_t toff[9];
+                {
+                    const uint32_t plane = a_stage_bytes >> 2;
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        const uint32_t ky = (uint32_t)(t / 3), kx = (uint32_t)(t % 3);
+                        toff[t] = p.halo == 2 ? ((ky & 1u) * 2u + (kx & 1u)) * plane + (ky >> 1) * pitch + (kx >> 1) * rb
+                                              : ky * pitch + kx * rb;
+                    }
+                }
                 int sa = 0; uint32_t pha = 0;
                 TcSched sch = sched_init<false>(p, w_first, w_step);
                 int w, seg0, seg1;
@@ -593,11 +621,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             const uint32_t b0 = smemB + (uint32_t)cb * b_bytes, bstep = (uint32_t)cblocks * b_bytes;
 #pragma unroll
                             for (int t = 0; t < 9; ++t)
-                                issue_kb(d_tmem, lo(a_tile + (uint32_t)(t / 3) * pitch + (uint32_t)(t % 3) * rb), ahi,
-                                         lo(b0 + (uint32_t)t * bstep), (uint32_t)(cb | t));
+                                issue_kb(d_tmem, lo(a_tile + toff[t]), ahi, lo(b0 + (uint32_t)t * bstep), (uint32_t)(cb | t));
                         } else {
+#pragma unroll
                             for (int ky = 0; ky < 3; ++ky) {        // one filter row = three K-blocks of straight-line code
-                                const uint32_t a_row = a_tile + (uint32_t)ky * pitch;
                                 // each stage is waited for right in front of its own MMAs and released right behind them (a commit
                                 // covers everything issued before it).  Waiting for all three stages first made a 5-stage ring stall
                                 // once per batch: only two of the next three stages can be in flight while a batch executes
@@ -606,7 +633,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                                 for (int kx = 0; kx < 3; ++kx) {
                                     wait_full(stage, phase);
                                     tc_fence_after();
-                                    issue_kb(d_tmem, lo(a_row + (uint32_t)kx * rb), ahi, lo(smem0 + (uint32_t)stage * stage_bytes),
+                                    issue_kb(d_tmem, lo(a_tile + toff[ky * 3 + kx]), ahi, lo(smem0 + (uint32_t)stage * stage_bytes),
                                              (uint32_t)(cb | ky | kx));
                                     release(empty_bar(stage));
                                     if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -649,8 +676,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     if (++acc == TC_ACC) { acc = 0; acc_phase ^= 1u; }
                 }
             }
-            if (ST && p.stats) { p.stats[blockIdx.x * 8 + 2] = (unsigned long long)w_full; p.stats[blockIdx.x * 8 + 3] = (unsigned long long)w_tempty;
-                                 p.stats[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_begin); }
+            if (ST && p.stats) { p.stats[blockIdx.x * 16 + 2] = (unsigned long long)w_full; p.stats[blockIdx.x * 16 + 3] = (unsigned long long)w_tempty;
+                                 p.stats[blockIdx.x * 16 + 4] = (unsigned long long)(clock64() - t_begin); }
         };
         if (leader && elect_one()) {
             auto by_kk = [&](auto kind_c) {
@@ -678,8 +705,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         int acc = p.epi_alt ? half : 0; uint32_t acc_phase = 0;
         uint32_t epi_res_phase = 0;               // TMA epilogue: parity of this group's residual barrier
         bool res_requested = false;               // TMA epilogue: the residual tile of the slab about to be processed is on its way
+        int out_buf = 0;                          // TMA epilogue: which of the group's epi_bufs OUT tiles the next slab uses
         int tile_cnt = 0;
-        long long w_tfull = 0; const long long t_begin = ST ? clock64() : 0;
+        long long w_tfull = 0, w_res = 0; const long long t_begin = ST ? clock64() : 0;
         TcSched sch = sched_init<KS>(p, w_first, w_step);
         int w, seg0, seg1;
         while (sched_next<KS>(sch, w, seg0, seg1)) {
@@ -948,10 +976,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             // the 128B swizzle, written by one thread per row and stored by one cp.async.bulk.tensor
             auto tma_store_f32_slab = [&](const float (&y)[32], int f0) {
                 const int g = half;
-                const uint32_t out_tile = stg_base + (uint32_t)g * 16384u;
+                const uint32_t out_tile = stg_base + (uint32_t)(g * p.epi_bufs + out_buf) * 16384u;
                 const bool boss = (q == 0) && (lane == 0);
                 const uint32_t rsw = (uint32_t)(r & 7), row_off = (uint32_t)r * 128u;
-                if (boss) tma_store_wait_read0();                      // the previous store has finished reading the tile
+                if (boss) { if (p.epi_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read0(); }   // the store that last used this tile has finished reading it
+                if (p.epi_bufs == 2) out_buf ^= 1;
                 named_bar_sync(1 + g, 128);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -979,7 +1008,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     constexpr int SW = 32 * NV;
                     constexpr uint32_t tile_bytes = 128u * SW * 2u, rowb = SW * 2u;
                     const int g = half;
-                    const uint32_t out_tile = stg_base + (uint32_t)g * (2u * tile_bytes), res_tile = out_tile + tile_bytes;
+                    const uint32_t grp_base = stg_base + (uint32_t)g * ((uint32_t)(p.epi_bufs + 1) * tile_bytes);   // [OUT x epi_bufs][RES]
+                    const uint32_t res_tile = grp_base + (uint32_t)p.epi_bufs * tile_bytes;
                     const bool boss = (q == 0) && (lane == 0);           // issues this group's TMA traffic
                     const int x0 = (m % p.xt) * p.TW, J0 = (m / p.xt) * p.TH + p.jshift;
                     const uint32_t rsw = (NV == 2) ? (uint32_t)(r & 7) : (uint32_t)((r >> 1) & 3);
@@ -1013,7 +1043,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                                 v[h2][j] = __float_as_uint(leaky ? fmaxf(a0, 0.1f * a0) : a0);
                             }
                         if (has_res) {
-                            mbar_wait(resfull_bar(g), epi_res_phase, 7);
+                            if constexpr (ST) { const long long c0 = clock64(); mbar_wait(resfull_bar(g), epi_res_phase, 7); w_res += clock64() - c0; }
+                            else mbar_wait(resfull_bar(g), epi_res_phase, 7);
                             epi_res_phase ^= 1u;
 #pragma unroll
                             for (int c = 0; c < 4 * NV; ++c) {             // own row of the residual tile, 16 bytes at a time
@@ -1031,8 +1062,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                                 }
                             }
                         }
-                        // the previous slab's TMA store must have finished READING the OUT tile before it is overwritten
-                        if (boss) tma_store_wait_read0();
+                        // the TMA store that last used this OUT tile must have finished READING it before it is overwritten
+                        const uint32_t out_tile = grp_base + (uint32_t)out_buf * tile_bytes;
+                        if (boss) { if (p.epi_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read0(); }
+                        if (p.epi_bufs == 2) out_buf ^= 1;
                         named_bar_sync(1 + g, 128);
                         if (has_res && boss) {                             // everybody is done with the RES tile: request the next one
                             if (f0 + SW < cend) request_res(w, f0 + SW);
@@ -1313,7 +1346,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             else if (++acc == TC_ACC) { acc = 0; acc_phase ^= 1u; }
         }
         if ((EPI == 1 || (EPI == 2 && p.tma_epi)) && (warp & 3) == 0 && lane == 0) tma_store_wait_all();   // this group's bulk stores have completed
-        if (ST && p.stats && warp == 2 && lane == 0) { p.stats[blockIdx.x * 8 + 5] = (unsigned long long)w_tfull; p.stats[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - t_begin); }
+        if (ST && p.stats && warp == 2 && lane == 0) { p.stats[blockIdx.x * 16 + 5] = (unsigned long long)w_tfull; p.stats[blockIdx.x * 16 + 6] = (unsigned long long)(clock64() - t_begin);
+                                                       p.stats[blockIdx.x * 16 + 8] = (unsigned long long)w_res; }
     }
 
     tc_fence_before();
@@ -1575,7 +1609,12 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
     const bool i8 = kind == 1 || kind == 2;
     const int esz = kind == 3 ? 4 : i8 ? 1 : 2;              // operand element size
     const int cin = i8 ? in.ldc : l.c;                       // s8: channels padded with zeros in both operands
-    const int BK = kind == 3 ? pick_bk_f32(l.c) : i8 ? pick_bk_i8(cin) : pick_bk(l.c), BN = pick_bn(l.n);
+    // stride-2 parity halo (TcParams::halo == 2): bf16, C <= 64 -- the layers whose per-tap activation boxes kept the TMA unit,
+    // not the tensor pipe, busy.  BK = 32 keeps three activation stages (4 planes x 9 x 17 lines each) inside shared memory.
+    const int s2h_maxc = getenv("YB_TC_S2_HALO_MAXC") ? atoi(getenv("YB_TC_S2_HALO_MAXC")) : 64;
+    const bool s2halo = kind == 0 && l.stride == 2 && l.size == 3 && l.pad == 1 && l.c % 32 == 0 && l.c <= s2h_maxc && !no_halo &&
+                        !getenv("YB_TC_NO_HALO");
+    const int BK = kind == 3 ? pick_bk_f32(l.c) : i8 ? pick_bk_i8(cin) : (s2halo && l.c <= 64) ? 32 : pick_bk(l.c), BN = pick_bn(l.n);
     p.kind = kind; p.alpha1 = alpha1; p.acc_out = acc_out;
     p.kk = BK * esz / 32;
     const bool s2 = l.stride == 2;
@@ -1613,16 +1652,21 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
     p.nt = (l.n + BN - 1) / BN;
     // everything that depends on the tile shape, for one candidate (halo or per-tap) -- returns the predicted kernel time
     // in cycles: waves x K-blocks x max(tensor / issue time, TMA time at the ~48 B/clk/SM a streaming kernel sustains)
+    // BN = 128 halo layers as CTA pairs too (experiment): 0 never, 1 the stride-2 one, 2 all.  Measured: no gain on 64->128 s2 @304,
+    // +25 % TIME on 64->128 s1 @152 (profiles/r02_notes.md) -- stays off.
+    const int cg2_bn128 = getenv("YB_TC_CG2_BN128") ? atoi(getenv("YB_TC_CG2_BN128")) : 0;
     auto layout = [&](bool halo) -> double {
-        p.halo = halo ? 1 : 0;
+        p.halo = halo ? (s2 ? 2 : 1) : 0;
         if (halo) { p.TW = 8; p.TH = 16; } else { p.TW = bestTW; p.TH = 128 / bestTW; }
         p.TWlog2 = 0; while ((1 << p.TWlog2) < p.TW) ++p.TWlog2;
-        p.jshift = halo ? 1 : 0;     // halo tiles start one merged row down: row 0 is a border row, and 2x2 windows then never straddle tiles
+        p.jshift = (halo && !s2) ? 1 : 0;     // halo tiles start one merged row down: row 0 is a border row, and 2x2 windows then never straddle tiles
         p.xt = (p.OW + p.TW - 1) / p.TW;
         p.jt = (int)((rows - p.jshift + p.TH - 1) / p.TH);
         p.num_tiles = p.xt * p.jt * p.nt;
         // CTA pairs (cta_group::2) for the wide tiles: halves the B bytes each SM has to pull through its TMA unit
-        p.cg = ((kind == 0 || ((kind == 1 || kind == 2) && !getenv("YB_TC_I8_CG1"))) && BN == 256 && p.xt * p.jt >= 2 &&
+        // (and for the BN = 128 stride-2 halo layer, whose 18 filter tiles per pixel tile otherwise outweigh the activation bytes)
+        p.cg = ((kind == 0 || ((kind == 1 || kind == 2) && !getenv("YB_TC_I8_CG1"))) &&
+                (BN == 256 || (BN == 128 && halo && cg2_bn128 >= (s2 ? 1 : 2))) && p.xt * p.jt >= 2 &&
                 !(cg_env && atoi(cg_env) == 1)) ? 2 : 1;
         p.num_work = (p.cg == 2) ? ((p.xt * p.jt + 1) / 2) * p.nt : p.num_tiles;
         p.a_bytes = (uint32_t)(TC_BM * BK * esz);
@@ -1630,8 +1674,8 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
         // small filter matrices stay resident in shared memory for the whole kernel (one TMA pass per CTA)
         p.bstat = (p.cg == 1 && p.nt == 1 && (size_t)p.kblocks * p.b_bytes <= 72 * 1024 && !getenv("YB_TC_NO_BSTAT")) ? 1 : 0;
         p.bstat_bytes = p.bstat ? (uint32_t)p.kblocks * p.b_bytes : 0u;
-        p.halo_pitch = (uint32_t)(p.TW + 2) * row_bytes;
-        p.halo_bytes = halo ? (uint32_t)(p.TH + 2) * p.halo_pitch : 0u;
+        p.halo_pitch = (uint32_t)(p.TW + (s2 ? 1 : 2)) * row_bytes;
+        p.halo_bytes = !halo ? 0u : s2 ? 4u * (uint32_t)(p.TH + 1) * p.halo_pitch : (uint32_t)(p.TH + 2) * p.halo_pitch;   // TMA bytes per tile and channel block
         const double mma = (double)p.kk * std::max(128.0 * BN / 256.0, 60.0);       // per K-block: tensor time vs single-thread issue
         const double a_per_kb = halo ? (double)p.halo_bytes / 9.0 : (double)p.a_bytes;
         const double tma = (a_per_kb + (p.bstat ? 0.0 : (double)p.b_bytes)) / 48.0;
@@ -1644,8 +1688,11 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
     // (8 KB tiles: no more shared memory than the LSU staging, so the rings stay deep) for the deep-K and the BN = 64 layers
     p.tma_epi = 0;
     const bool i8kind = kind == 1 || kind == 2;
-    if (kind == 0 && out_bf16 && !s2 && BN >= 32 && !no_halo && !getenv("YB_TC_NO_TMA_EPI") && !getenv("YB_TC_NO_COALESCE") &&
-        (!res.base || res_bf16)) {
+    // (stride-2 layers keep the LSU epilogue: their tiles walk the input's merged half-rows, OH + 1 per image, while the output has
+    // OH + 2 rows per image -- a per-image (c, x, y, image) store would need a negative start row for the second image of a
+    // straddling tile, and bulk tensor STORES fault on negative coordinates: tools/probes/tma4d_probe.cu, profiles/r02_tma4d_probe.txt)
+    if (kind == 0 && out_bf16 && !s2 && BN >= 32 && !no_halo && !getenv("YB_TC_NO_TMA_EPI") &&
+        !getenv("YB_TC_NO_COALESCE") && (!res.base || res_bf16)) {
         p.tma_epi = (BN >= 128 && p.kblocks <= 24) ? 64 : 32;   // measured per layer class (profiles/r02_notes.md)
         if (getenv("YB_TC_TMA_EPI_SW")) p.tma_epi = (atoi(getenv("YB_TC_TMA_EPI_SW")) == 64 && BN >= 128) ? 64 : 32;
     }
@@ -1655,12 +1702,19 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
     // BN = 32 tiles have a single 32-column slab, so alternating is the only way to use both groups at all
     p.epi_alt = ((BN == 32 && (kind == 0 || i8kind)) || (p.tma_epi && (BN <= 64 || getenv("YB_TC_EPI_ALT_128")) && BN <= 128)) &&
                 !getenv("YB_TC_NO_EPI_ALT") ? 1 : 0;
-    const size_t ring_budget = (size_t)(p.tma_epi == 64 ? 158 : 191) * 1024;   // what is left of 227 KB beside the epilogue tiles
+    // (experiment, YB_TC_EPI_BUFS=2: two OUT tiles per group.  Measured: no layer gains, the layers that lose ring stages slow down
+    // by 11-15 % -- the store's read latency is not what the slab loop waits for; profiles/r02_notes.md)
+    p.epi_bufs = (getenv("YB_TC_EPI_BUFS") && p.tma_epi && atoi(getenv("YB_TC_EPI_BUFS")) == 2) ? 2 : 1;
+    const size_t epi_tile = i8kind ? 16384 : (size_t)128 * p.tma_epi * 2;
+    const size_t epi_tiles_bytes = !p.tma_epi ? 0 : i8kind ? 2 * p.epi_bufs * epi_tile : 2 * (p.epi_bufs + 1) * epi_tile;
+    // what is left of 227 KB beside the epilogue tiles (5 KB: barriers, bias, alignment slack)
+    const size_t ring_budget = p.tma_epi ? (size_t)(227 - 5) * 1024 - std::max<size_t>(epi_tiles_bytes, 32 * 1024) : (size_t)191 * 1024;
     bool use_halo = false;
     if (l.size == 3 && l.stride == 1 && l.pad == 1 && !no_halo && !getenv("YB_TC_NO_HALO") && (kind == 0 || ((kind == 1 || kind == 2) && !getenv("YB_TC_I8_NO_HALO")))) {
         const double t_halo = layout(true), t_tap = layout(false);
         use_halo = t_halo < 0.97 * t_tap || want_halo || getenv("YB_TC_HALO") != nullptr;   // want_halo: a fused max-pool needs the 8 x 16 tiles
     }
+    if (s2halo) use_halo = true;
     layout(use_halo);
     // several K-blocks per stage when they are small: the single MMA-issuing thread pays a fixed barrier round
     // trip per stage, which dominated the C<=64 layers (profiles/r01_notes.md)
@@ -1675,7 +1729,7 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
     const size_t fixed_smem = sizeof(float) * (size_t)p.nt * BN;
     p.a_stages = 0; p.a_stage_bytes = 0;
     if (p.halo) {
-        p.a_stage_bytes = (p.halo_bytes + 1023u) & ~1023u;
+        p.a_stage_bytes = p.halo == 2 ? 4u * ((p.halo_bytes / 4u + 1023u) & ~1023u) : (p.halo_bytes + 1023u) & ~1023u;
         const int want = getenv("YB_TC_ASTAGES") ? atoi(getenv("YB_TC_ASTAGES")) : 3;
         p.a_stages = std::max(2, std::min(TC_MAX_ASTAGES, want));
         // keep at least 4 filter stages beside the activation ring
@@ -1738,7 +1792,7 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
         cuuint64_t dims[5] = {(cuuint64_t)cin, 2, (cuuint64_t)in.Wp / 2, 2, (cuuint64_t)in.N * in.Hp / 2};
         cuuint64_t strides[4] = {(cuuint64_t)in.ldc * esz, (cuuint64_t)in.ldc * 2 * esz, (cuuint64_t)in.Wp * in.ldc * esz,
                                  (cuuint64_t)in.Wp * in.ldc * 2 * esz};
-        cuuint32_t box[5] = {(cuuint32_t)BK, 1, (cuuint32_t)p.TW, 1, (cuuint32_t)p.TH};
+        cuuint32_t box[5] = {(cuuint32_t)BK, 1, (cuuint32_t)(p.halo ? p.TW + 1 : p.TW), 1, (cuuint32_t)(p.halo ? p.TH + 1 : p.TH)};
         cuuint32_t es[5] = {1, 1, 1, 1, 1};
         r = enc(&plan->tmA, dtype, 5, in.base, dims, strides, box, es,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1775,13 +1829,13 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
     plan->pdl = (getenv("YB_NO_PDL") == nullptr) ? 1 : 0;
     plan->grid = (p.cg == 2) ? 2 * std::min(p.num_work, sms / 2) : std::min(p.num_tiles, sms);
     if (getenv("YB_TC_STATS")) {
-        cudaMalloc(&p.stats, sizeof(unsigned long long) * 8 * plan->grid);
-        cudaMemset(p.stats, 0, sizeof(unsigned long long) * 8 * plan->grid);
+        cudaMalloc(&p.stats, sizeof(unsigned long long) * 16 * plan->grid);
+        cudaMemset(p.stats, 0, sizeof(unsigned long long) * 16 * plan->grid);
     }
     plan->smem = (size_t)p.stages * p.stage_bytes + a_ring + p.bstat_bytes + 1024 /*alignment slack*/ +
                  8 * (2 * p.stages + 2 * TC_ACC + 1 + 2 * TC_MAX_ASTAGES + 2) + 16 +
                  sizeof(float) * (size_t)p.nt * BN /*bias*/ + (size_t)p.nt * BN / 8 /*yolo mask*/ +
-                 (p.tma_epi ? 1024 + 4 * (size_t)(128 * p.tma_epi * 2) /*TMA epilogue: [OUT | RES] tile per warp group*/
+                 (p.tma_epi ? 1024 + std::max<size_t>(epi_tiles_bytes, 4 * (size_t)(128 * p.tma_epi * 2)) /*TMA epilogue: [OUT x bufs | RES] per warp group*/
                             : 128 + 4096 * TC_EPI_WARPS /*epilogue staging*/);
     if (plan->smem > 227 * 1024) { delete plan; fatal_throw("tc plan: shared memory budget exceeded"); }
     {
@@ -1992,14 +2046,14 @@ void tc_launch(void *vp, cudaStream_t s) {
 void tc_free_plan(void *vp) {
     TcPlan *plan = reinterpret_cast<TcPlan *>(vp);
     if (plan && plan->p.stats) {   // diagnostic dump: mean cycles per CTA of the LAST launch
-        std::vector<unsigned long long> h(8 * (size_t)plan->grid);
+        std::vector<unsigned long long> h(16 * (size_t)plan->grid);
         cudaDeviceSynchronize();
         cudaMemcpy(h.data(), plan->p.stats, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-        double m[8] = {0};
-        for (int b = 0; b < plan->grid; ++b) for (int k = 0; k < 8; ++k) m[k] += (double)h[8 * b + k] / plan->grid;
+        double m[16] = {0};
+        for (int b = 0; b < plan->grid; ++b) for (int k = 0; k < 16; ++k) m[k] += (double)h[16 * b + k] / plan->grid;
         fprintf(stderr, "TCSTATS %-28s cg %d tiles/cta %.1f kb %d sps %d BN %d ksplit T%d L%d/%d | producer: wait_empty %.0f tma_issue %.0f total %.0f | mma: wait_full %.0f "
-                        "wait_tempty %.0f total %.0f | epi: wait_tfull %.0f total %.0f\n", plan->desc, plan->p.cg,
-                (double)plan->p.num_tiles / plan->grid * 1.0, plan->p.kblocks, plan->p.sps, plan->p.BN, plan->p.sk_T, plan->p.sk_L, plan->p.kbs, m[0], m[7], m[1], m[2], m[3], m[4], m[5], m[6]);
+                        "wait_tempty %.0f total %.0f | epi: wait_tfull %.0f wait_res %.0f total %.0f\n", plan->desc, plan->p.cg,
+                (double)plan->p.num_tiles / plan->grid * 1.0, plan->p.kblocks, plan->p.sps, plan->p.BN, plan->p.sk_T, plan->p.sk_L, plan->p.kbs, m[0], m[7], m[1], m[2], m[3], m[4], m[5], m[8], m[6]);
         cudaFree(plan->p.stats);
     }
     delete plan;
