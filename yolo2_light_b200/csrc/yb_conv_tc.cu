@@ -1700,7 +1700,9 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
     if (i8kind && !s2 && !acc_out && !getenv("YB_TC_NO_TMA_EPI") && !getenv("YB_TC_NO_COALESCE")) p.tma_epi = 32;
     // alternate tiles per group: -24 % on 32->64 3x3 @304, -17 % on the BN = 64 1x1 layers, but +5 % on BN = 128 (measured);
     // BN = 32 tiles have a single 32-column slab, so alternating is the only way to use both groups at all
-    p.epi_alt = ((BN == 32 && (kind == 0 || i8kind)) || (p.tma_epi && (BN <= 64 || getenv("YB_TC_EPI_ALT_128")) && BN <= 128)) &&
+    // (and the BN = 64 stride-2 layer on the LSU epilogue: epilogue-bound once its loads are halo tiles -- 150 k of 176 k cycles busy)
+    p.epi_alt = ((BN == 32 && (kind == 0 || i8kind)) || (p.tma_epi && (BN <= 64 || getenv("YB_TC_EPI_ALT_128")) && BN <= 128) ||
+                 (kind == 0 && s2 && BN == 64 && out_bf16 && !getenv("YB_TC_NO_EPI_ALT_S2"))) &&
                 !getenv("YB_TC_NO_EPI_ALT") ? 1 : 0;
     // (experiment, YB_TC_EPI_BUFS=2: two OUT tiles per group.  Measured: no layer gains, the layers that lose ring stages slow down
     // by 11-15 % -- the store's read latency is not what the slab loop waits for; profiles/r02_notes.md)
