@@ -439,7 +439,7 @@ void quantinization_and_get_multipliers(Network *net) {
 // correct_yolo_boxes (:4281), do_nms_sort (box.c:296).
 // ------------------------------------------------------------------------------------------------------
 namespace {
-struct Det { float x, y, w, h, objectness; std::vector<float> prob; int sort_class = 0; };
+struct Det { float x, y, w, h, objectness; std::vector<float> prob; int sort_class = 0; int order = 0; };
 
 float overlap(float x1, float w1, float x2, float w2) {
     float l1 = x1 - w1 / 2, l2 = x2 - w2 / 2;
@@ -542,10 +542,15 @@ int get_boxes(const Network *net, int b, int w, int h, float thresh, float nms, 
             if (dets[i].objectness == 0) { std::swap(dets[i], dets[k]); --k; --i; }
         }
         total = k + 1;
+        // Equal probabilities (they do occur: bf16 activations collide) are ordered by position in the candidate list, for every
+        // class -- the same rule as the device path (k_det_nms, yb_detect.cuh).  The reference leaves it to qsort (box.c:311),
+        // whose tie order is unspecified and differs between C libraries.
+        for (int i = 0; i < total; ++i) dets[i].order = i;
         for (int c = 0; c < classes; ++c) {
             for (int i = 0; i < total; ++i) dets[i].sort_class = c;
-            std::stable_sort(dets.begin(), dets.begin() + total,
-                             [c](const Det &a, const Det &b2) { return a.prob[c] > b2.prob[c]; });
+            std::sort(dets.begin(), dets.begin() + total, [c](const Det &a, const Det &b2) {
+                return a.prob[c] > b2.prob[c] || (a.prob[c] == b2.prob[c] && a.order < b2.order);
+            });
             for (int i = 0; i < total; ++i) {
                 if (dets[i].prob[c] == 0) continue;
                 for (int j = i + 1; j < total; ++j)
