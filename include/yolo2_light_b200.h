@@ -236,7 +236,9 @@ int yb_network_profile(yb_network *net, int quantized, const void *d_input, int 
 /* ---- detection decode (host) -------------------------------------------------------- */
 
 /* replaces get_network_boxes + do_nms_sort   src/additionally.c:4403, src/box.c:296 for batch item b.
- * out rows: {x, y, w, h, objectness, prob[classes]}; returns the number of rows written (<= max_rows). */
+ * out rows: {x, y, w, h, objectness, prob[classes]}; returns the number of rows written (<= max_rows).
+ * Candidates with EQUAL class probability are ranked by their position in the candidate list (layer, cell, anchor), here and
+ * in yb_network_detect; the reference leaves their order to qsort (box.c:311), i.e. to the C library. */
 int yb_get_network_boxes(const yb_network *net, int b, int w, int h, float thresh, float nms, int relative,
                          int letter, float *out, int max_rows);
 
