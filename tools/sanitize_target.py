@@ -11,7 +11,9 @@ jobs = [("tcnet", test_gpu_tc.tcnet(64), 0), ("tiny", cfgs.slim(cfgs.yolov3_tiny
         ("xnor", cfgs.slim(cfgs.tiny_yolo_obj_xnor, 2, 64, 64), 0), ("spp", cfgs.slim(cfgs.yolov3_spp, 4, 32, 32), 0),
         # full-width tiny models: fused stem + pool, pool-fused integer epilogues, narrow XNOR layers as +-1 on kind::i8
         ("tiny_full", cfgs.yolov3_tiny(64, 64), 1), ("xnor_full", cfgs.tiny_yolo_obj_xnor(64, 64), 0),
-        ("v3_full", cfgs.slim(cfgs.yolov3, 2, 64, 64), 0)]
+        ("v3_full", cfgs.slim(cfgs.yolov3, 2, 64, 64), 0),
+        # stride-2 parity-halo tiles (C = 32 with resident filters, C = 64 over two channel blocks), non-square
+        ("s2net", test_gpu_tc.s2net(), 0)]
 for name, secs, q in jobs:
     cfg = cfgs.write_cfg(secs, os.path.join(wd, name + ".cfg")); wts = cfgs.write_weights(secs, os.path.join(wd, name + ".weights"), seed=3)
     size = int(secs[0][1]["width"])
