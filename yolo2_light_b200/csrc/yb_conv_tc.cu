@@ -90,6 +90,7 @@ struct TcParams {
     // bf16 into a 128B-swizzled shared-memory tile and one thread stores it with cp.async.bulk.tensor; the shortcut residual
     // comes in the same way (TMA load + mbarrier).  No shuffles, no staging transposes, no LSU global traffic, ~100 registers.
     int tma_epi;
+    int l2_hint;              // 1: halo activation tiles and shortcut tiles are loaded with the L2 evict-first policy
     // epi_alt (with tma_epi, BN <= 128): the two groups of four epilogue warps take ALTERNATE tiles (group g: accumulator g, all
     // BN columns) instead of half the columns of every tile -- two tiles are in the epilogue at once; the per-tile epilogue of the
     // small tiles is a latency chain (TMEM load -> math -> barrier -> store), not a throughput problem.
@@ -167,6 +168,18 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm,
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// L2 eviction hint for data that is dead after this kernel (the C/2 tensor a 3x3 layer reads, the shortcut operand): evict-first
+// leaves the L2 to the output this kernel writes, which the next layer reads right away
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_3d_hint(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1) {
     asm volatile(
@@ -262,6 +275,11 @@ __device__ __forceinline__ void tma2_load_3d(uint32_t dst, const CUtensorMap *tm
     asm volatile(
         "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(dst), "l"(tm), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d_hint(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"(tm), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1) {
     asm volatile(
@@ -448,6 +466,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 const int SA = p.a_stages;
                 const uint32_t a_stage_bytes = p.a_stage_bytes, halo_bytes = p.halo_bytes;
                 int sa = 0; uint32_t pha = 0;
+                const uint64_t pol_first = l2_policy_evict_first();
                 TcSched schA = sched_init<false>(p, w_first, w_step);
                 int wA = 0, cbA = cblocks, d0, d1;
                 auto next_A = [&]() {
@@ -466,6 +485,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             if constexpr (CG == 2) tma2_load_5d(ad + (uint32_t)pl * plane, &tmA, fb, cbA * BK, pl & 1, x0, pl >> 1, J0);
                             else tma_load_5d(ad + (uint32_t)pl * plane, &tmA, fb, cbA * BK, pl & 1, x0, pl >> 1, J0);
                         }
+                    } else if (p.l2_hint) {
+                        if constexpr (CG == 2) tma2_load_3d_hint(ad, &tmA, fb, cbA * BK, x0, J0 - 1, pol_first);
+                        else tma_load_3d_hint(ad, &tmA, fb, cbA * BK, x0, J0 - 1, pol_first);
                     } else if constexpr (CG == 2) tma2_load_3d(ad, &tmA, fb, cbA * BK, x0, J0 - 1);
                     else tma_load_3d(ad, &tmA, fb, cbA * BK, x0, J0 - 1);
                     ++cbA;
@@ -1021,7 +1043,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     auto request_res = [&](int w_, int f_) {
                         const int m_ = (CG == 2) ? 2 * (w_ / p.nt) + (int)rank : w_ / p.nt;
                         mbar_arrive_expect_tx(resfull_bar(g), tile_bytes);
-                        tma_load_3d(res_tile, &tmR, resfull_bar(g), (w_ % p.nt) * p.BN + f_, (m_ % p.xt) * p.TW + 1, (m_ / p.xt) * p.TH + p.jshift);
+                        if (p.l2_hint) tma_load_3d_hint(res_tile, &tmR, resfull_bar(g), (w_ % p.nt) * p.BN + f_, (m_ % p.xt) * p.TW + 1, (m_ / p.xt) * p.TH + p.jshift, l2_policy_evict_first());
+                        else tma_load_3d(res_tile, &tmR, resfull_bar(g), (w_ % p.nt) * p.BN + f_, (m_ % p.xt) * p.TW + 1, (m_ / p.xt) * p.TH + p.jshift);
                     };
                     if (has_res && boss && !res_requested) request_res(w, cbeg);   // very first slab of this group
                     res_requested = true;
@@ -1769,6 +1792,7 @@ static void *make_plan_common(int kind, const Layer &l, const TV &in, const TV &
     if (res.base && res_bf16 && (res.ldc % 8 != 0 || (reinterpret_cast<uintptr_t>(res.base) & 15))) fatal_throw("tc plan: residual alignment");
     p.bias = d_bias; p.act = l.activation; p.act2 = act2;
     p.dbg = getenv("YB_TC_DBG") ? atoi(getenv("YB_TC_DBG")) : 0;
+    p.l2_hint = (kind == 0 && !getenv("YB_TC_NO_L2_HINT")) ? 1 : 0;
     p.no_coalesce = getenv("YB_TC_NO_COALESCE") ? 1 : 0;
     snprintf(plan->desc, sizeof(plan->desc), "%dx%dx%d -> n%d k%d s%d%s%s", l.c, l.h, l.w, l.n, l.size, l.stride, p.halo ? " halo" : "",
              p.tma_epi ? " tepi" : "");
